@@ -1,0 +1,517 @@
+// capi.cu -- the C ABI of include/tfhe_b200.h: context, key ingestion, batched entry points.
+// No CPU fallback anywhere in this file: every entry point launches sm_100a kernels or fails.
+#include "engine.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <mutex>
+
+using namespace tfhe_b200;
+
+struct tfhe_b200_ctx {
+    int device = -1;
+    int sm_count = 0;
+    std::string err;
+    // FFT tables per ring degree
+    cplx* tw1024 = nullptr;
+    cplx* tw2048 = nullptr;
+    // gate keys
+    bool gate_ready = false;
+    tfhe_b200_gate_params gp{};
+    cplx* g_bkfft = nullptr;  size_t g_bkfft_bytes = 0;
+    int32_t* g_ks = nullptr;  size_t g_ks_bytes = 0;
+    // circuit-bootstrap keys
+    bool cb_ready = false;
+    tfhe_b200_cb_params cp{};
+    cplx* c_bkfft = nullptr;
+    int32_t* c_preks = nullptr;
+    int32_t* c_privks = nullptr;    // [2][rows][t][base-1][2*N1]
+    size_t c_privks_u_stride = 0;   // int32 elements per u
+    // hp tables
+    uint64_t* hp_omega[2] = {nullptr, nullptr};   // N = 2048, 4096
+    uint64_t* hp_ombar[2] = {nullptr, nullptr};
+    // scratch (grown on demand, never per call once warm)
+    void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[4] = {0, 0, 0, 0};
+};
+
+static std::string g_create_err;
+static std::mutex g_mu;
+
+static int fail(tfhe_b200_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else { std::lock_guard<std::mutex> l(g_mu); g_create_err = msg; }
+    return code;
+}
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(ctx, TFHE_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+#define NEED(cond, msg) do { if (!(cond)) return fail(ctx, TFHE_B200_ERR_PARAM, msg); } while (0)
+
+static int ensure_scratch(tfhe_b200_ctx* ctx, int slot, size_t bytes) {
+    if (ctx->scratch_bytes[slot] >= bytes) return TFHE_B200_OK;
+    if (ctx->scratch[slot]) { CU(cudaFree(ctx->scratch[slot])); ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0; }
+    size_t want = bytes + bytes / 8;
+    CU(cudaMalloc(&ctx->scratch[slot], want));
+    ctx->scratch_bytes[slot] = want;
+    return TFHE_B200_OK;
+}
+
+static int upload_tw(tfhe_b200_ctx* ctx, int logM, cplx** dst) {
+    const int ne = fft_table_entries(logM);
+    std::vector<double> h((size_t)ne * 2);
+    make_fft_tables(logM, h.data());
+    CU(cudaMalloc(dst, sizeof(cplx) * ne));
+    CU(cudaMemcpy(*dst, h.data(), sizeof(cplx) * ne, cudaMemcpyHostToDevice));
+    return TFHE_B200_OK;
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int tfhe_b200_ctx_create(tfhe_b200_ctx** out, int device) {
+    tfhe_b200_ctx* ctx = nullptr;   // for the CU macro: errors go to the global slot
+    if (!out) return fail(nullptr, TFHE_B200_ERR_PARAM, "ctx_create: null output pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, TFHE_B200_ERR_NODEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, TFHE_B200_ERR_PARAM, "ctx_create: device ordinal out of range");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, TFHE_B200_ERR_NODEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                                        ", this library carries sm_100a code only");
+    CU(cudaSetDevice(device));
+    tfhe_b200_ctx* c = new tfhe_b200_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    ctx = c;
+    int rc;
+    if ((rc = upload_tw(ctx, 9, &c->tw1024)) != TFHE_B200_OK || (rc = upload_tw(ctx, 10, &c->tw2048)) != TFHE_B200_OK) {
+        fail(nullptr, rc, c->err); delete c; return rc;
+    }
+    e = blind_rotate_init();
+    if (e != cudaSuccess) { fail(nullptr, TFHE_B200_ERR_CUDA, std::string("blind_rotate_init: ") + cudaGetErrorString(e)); delete c; return TFHE_B200_ERR_CUDA; }
+    e = hp_init();
+    if (e != cudaSuccess) { fail(nullptr, TFHE_B200_ERR_CUDA, std::string("hp_init: ") + cudaGetErrorString(e)); delete c; return TFHE_B200_ERR_CUDA; }
+    *out = c;
+    return TFHE_B200_OK;
+}
+
+int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx) {
+    if (!ctx) return TFHE_B200_OK;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->tw1024); cudaFree(ctx->tw2048);
+    cudaFree(ctx->g_bkfft); cudaFree(ctx->g_ks);
+    cudaFree(ctx->c_bkfft); cudaFree(ctx->c_preks); cudaFree(ctx->c_privks);
+    for (int i = 0; i < 2; i++) { cudaFree(ctx->hp_omega[i]); cudaFree(ctx->hp_ombar[i]); }
+    for (int i = 0; i < 4; i++) cudaFree(ctx->scratch[i]);
+    delete ctx;
+    return TFHE_B200_OK;
+}
+
+const char* tfhe_b200_last_error(const tfhe_b200_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> l(g_mu);
+    return g_create_err.c_str();
+}
+int tfhe_b200_sm_count(const tfhe_b200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+int tfhe_b200_synchronize(tfhe_b200_ctx* ctx, void* stream) {
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+
+/* ------------------------------------------------------------------ gate keys */
+static int check_gate_params(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p) {
+    NEED(p, "gate params: null");
+    NEED(p->N == 1024, "gate params: only N = 1024 is compiled (TLweParams::N)");
+    NEED(p->k == 1, "gate params: k must be 1 (cb/poc_types.h:10)");
+    NEED(p->n >= 1 && p->n <= 1024, "gate params: n out of range [1,1024]");
+    NEED(p->bk_l >= 1 && p->bk_l * p->bk_Bgbit <= 32 && p->bk_Bgbit >= 1 && p->bk_Bgbit <= 16, "gate params: bad gadget (l, Bgbit)");
+    NEED(p->ks_basebit >= 1 && p->ks_basebit <= 3, "gate params: ks_basebit must be 1..3");
+    NEED(p->ks_t >= 1 && p->ks_t * p->ks_basebit <= 31, "gate params: ks_t * ks_basebit must be <= 31");
+    return TFHE_B200_OK;
+}
+static size_t gate_cols_pad(const tfhe_b200_gate_params& p) { return (size_t)((p.n + 1 + 511) / 512) * 512; }
+
+int tfhe_b200_gate_alloc_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    int rc = check_gate_params(ctx, p); if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->g_bkfft) { CU(cudaFree(ctx->g_bkfft)); ctx->g_bkfft = nullptr; }
+    if (ctx->g_ks) { CU(cudaFree(ctx->g_ks)); ctx->g_ks = nullptr; }
+    ctx->gate_ready = false;
+    ctx->gp = *p;
+    const size_t npoly = (size_t)p->n * 2 * p->bk_l * 2;
+    ctx->g_bkfft_bytes = npoly * (p->N / 2) * sizeof(cplx);
+    ctx->g_ks_bytes = (size_t)p->N * p->ks_t * ((1 << p->ks_basebit) - 1) * gate_cols_pad(*p) * sizeof(int32_t);
+    CU(cudaMalloc(&ctx->g_bkfft, ctx->g_bkfft_bytes));
+    CU(cudaMalloc(&ctx->g_ks, ctx->g_ks_bytes));
+    ctx->gate_ready = true;   // contents are the caller's responsibility on this path (broadcast receiver)
+    return TFHE_B200_OK;
+}
+
+int tfhe_b200_gate_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p, const int32_t* bk_host, const int32_t* ks_host) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(bk_host && ks_host, "gate_load_keys: null key pointer");
+    int rc = tfhe_b200_gate_alloc_keys(ctx, p); if (rc) return rc;
+    ctx->gate_ready = false;
+    const int N = p->N, base = 1 << p->ks_basebit;
+    const size_t npoly = (size_t)p->n * 2 * p->bk_l * 2;
+    // bk: coefficient domain -> spectra, scaled by 2/N so the backward transform needs no scaling
+    // (tGswToFFTConvert cb/tgsw_functions.cpp:389-394 ; the 2/N of execute_direct_torus32 :78-100 is folded in here)
+    int32_t* tmp = nullptr;
+    CU(cudaMalloc(&tmp, npoly * N * sizeof(int32_t)));
+    CU(cudaMemcpy(tmp, bk_host, npoly * N * sizeof(int32_t), cudaMemcpyHostToDevice));
+    cudaError_t e = launch_poly_to_spectrum32(ctx->g_bkfft, tmp, ctx->tw1024, N, (int)npoly, 2.0 / N, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(tmp);
+    CU(e);
+    // ks: drop d = 0 rows, pad rows to 512 columns
+    const size_t raw = (size_t)N * p->ks_t * base * (p->n + 1);
+    CU(cudaMalloc(&tmp, raw * sizeof(int32_t)));
+    CU(cudaMemcpy(tmp, ks_host, raw * sizeof(int32_t), cudaMemcpyHostToDevice));
+    e = launch_ks_repack(ctx->g_ks, tmp, N, p->ks_t, base, p->n + 1, (int)gate_cols_pad(*p), 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(tmp);
+    CU(e);
+    ctx->gate_ready = true;
+    return TFHE_B200_OK;
+}
+
+int tfhe_b200_gate_key_blob(tfhe_b200_ctx* ctx, int which, void** dev_ptr, size_t* bytes) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(dev_ptr && bytes, "gate_key_blob: null output");
+    if (!ctx->g_bkfft) return fail(ctx, TFHE_B200_ERR_NOKEY, "gate_key_blob: gate keys not allocated");
+    if (which == 0) { *dev_ptr = ctx->g_bkfft; *bytes = ctx->g_bkfft_bytes; }
+    else if (which == 1) { *dev_ptr = ctx->g_ks; *bytes = ctx->g_ks_bytes; }
+    else return fail(ctx, TFHE_B200_ERR_PARAM, "gate_key_blob: which must be 0 or 1");
+    return TFHE_B200_OK;
+}
+
+#define NEED_GATE() do { if (!ctx) return TFHE_B200_ERR_PARAM; if (!ctx->gate_ready) return fail(ctx, TFHE_B200_ERR_NOKEY, "gate keys not loaded"); } while (0)
+
+static BRArgs gate_br_args(const tfhe_b200_ctx* ctx, int count) {
+    BRArgs a{};
+    a.bkfft = ctx->g_bkfft; a.tw = ctx->tw1024;
+    a.n = ctx->gp.n; a.l = ctx->gp.bk_l; a.Bgbit = ctx->gp.bk_Bgbit; a.count = count;
+    a.out_stride = ctx->gp.N + 1;
+    a.n_mu = 1; a.mu_bgbit = 0;
+    return a;
+}
+
+int tfhe_b200_blindRotate_FFT_batch(tfhe_b200_ctx* ctx, int32_t* accum_dev, const int32_t* bara_dev, int count, void* stream) {
+    NEED_GATE(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (accum_dev && bara_dev), "null buffer");
+    BRArgs a = gate_br_args(ctx, count);
+    a.mode = BR_ACCUM; a.accum = accum_dev; a.bara = bara_dev;
+    CU(launch_blind_rotate32(a, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_blindRotateAndExtract_FFT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* v_dev, const int32_t* barb_dev,
+                                              const int32_t* bara_dev, int count, void* stream) {
+    NEED_GATE(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && v_dev && barb_dev && bara_dev), "null buffer");
+    BRArgs a = gate_br_args(ctx, count);
+    a.mode = BR_TESTVEC; a.v = v_dev; a.barb = barb_dev; a.bara = bara_dev; a.out = result_dev;
+    CU(launch_blind_rotate32(a, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+static int bootstrap_woks(tfhe_b200_ctx* ctx, int32_t* result_dev, int32_t mu, const int32_t* xa, const int32_t* xb, int ka, int kb,
+                          int32_t cconst, int count, cudaStream_t s) {
+    BRArgs a = gate_br_args(ctx, count);
+    a.mode = BR_LWE; a.xa = xa; a.xb = xb; a.ka = ka; a.kb = kb; a.cconst = cconst; a.mu = mu; a.out = result_dev;
+    CU(launch_blind_rotate32(a, s));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_bootstrap_woKS_FFT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, int32_t mu, const int32_t* x_dev, int count, void* stream) {
+    NEED_GATE(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && x_dev), "null buffer");
+    return bootstrap_woks(ctx, result_dev, mu, x_dev, nullptr, 1, 0, 0, count, (cudaStream_t)stream);
+}
+static int gate_keyswitch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* sample_dev, int count, cudaStream_t s) {
+    KSArgs k{};
+    k.in = sample_dev; k.in_stride = ctx->gp.N + 1; k.rows_in = ctx->gp.N; k.t = ctx->gp.ks_t; k.basebit = ctx->gp.ks_basebit;
+    k.key = ctx->g_ks; k.cols = ctx->gp.n + 1; k.cols_pad = (int)gate_cols_pad(ctx->gp);
+    k.b_col = ctx->gp.n; k.b_index = ctx->gp.N; k.out = result_dev; k.out_stride = ctx->gp.n + 1; k.count = count;
+    CU(launch_keyswitch32(k, s));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_lweKeySwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* sample_dev, int count, void* stream) {
+    NEED_GATE(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && sample_dev), "null buffer");
+    return gate_keyswitch(ctx, result_dev, sample_dev, count, (cudaStream_t)stream);
+}
+static int bootstrap_full(tfhe_b200_ctx* ctx, int32_t* result_dev, int32_t mu, const int32_t* xa, const int32_t* xb, int ka, int kb,
+                          int32_t cconst, int count, cudaStream_t s) {
+    const size_t ubytes = (size_t)count * (ctx->gp.N + 1) * sizeof(int32_t);
+    int rc = ensure_scratch(ctx, 0, ubytes); if (rc) return rc;
+    int32_t* u = (int32_t*)ctx->scratch[0];
+    rc = bootstrap_woks(ctx, u, mu, xa, xb, ka, kb, cconst, count, s); if (rc) return rc;
+    return gate_keyswitch(ctx, result_dev, u, count, s);
+}
+int tfhe_b200_bootstrap_FFT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, int32_t mu, const int32_t* x_dev, int count, void* stream) {
+    NEED_GATE(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && x_dev), "null buffer");
+    return bootstrap_full(ctx, result_dev, mu, x_dev, nullptr, 1, 0, 0, count, (cudaStream_t)stream);
+}
+
+/* boots* constants [UPSTREAM boot-gates.cpp, SURVEY Appendix C]: tmp = (0, c8/8) + ka*ca + kb*cb */
+static const struct { int c8, ka, kb; } kGate[TFHE_B200_NUM_GATES] = {
+    {1, -1, -1}, {-1, 1, 1}, {1, 1, 1}, {-1, -1, -1}, {2, 2, 2}, {-2, -2, -2}, {-1, -1, 1}, {-1, 1, -1}, {1, -1, 1}, {1, 1, -1},
+};
+static const int32_t kMU = 1 << 29;   // modSwitchToTorus32(1, 8)
+
+int tfhe_b200_bootsGate_batch(tfhe_b200_ctx* ctx, int op, int32_t* result_dev, const int32_t* ca_dev, const int32_t* cb_dev, int count, void* stream) {
+    NEED_GATE(); NEED(op >= 0 && op < TFHE_B200_NUM_GATES, "bootsGate: unknown gate");
+    NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && ca_dev && cb_dev), "null buffer");
+    return bootstrap_full(ctx, result_dev, kMU, ca_dev, cb_dev, kGate[op].ka, kGate[op].kb, (int32_t)((uint32_t)kGate[op].c8 * (uint32_t)kMU),
+                          count, (cudaStream_t)stream);
+}
+int tfhe_b200_bootsNOT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* ca_dev, int count, void* stream) {
+    NEED_GATE(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && ca_dev), "null buffer");
+    CU(launch_lwe_lincomb(result_dev, ca_dev, nullptr, -1, 0, 0, ctx->gp.n, count, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_bootsMUX_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* a_dev, const int32_t* b_dev, const int32_t* c_dev,
+                             int count, void* stream) {
+    NEED_GATE(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && a_dev && b_dev && c_dev), "null buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int N = ctx->gp.N;
+    const size_t ubytes = (size_t)count * (N + 1) * sizeof(int32_t);
+    int rc = ensure_scratch(ctx, 0, ubytes); if (rc) return rc;
+    rc = ensure_scratch(ctx, 1, ubytes); if (rc) return rc;
+    int32_t* u1 = (int32_t*)ctx->scratch[0]; int32_t* u2 = (int32_t*)ctx->scratch[1];
+    // AND(a,b) and AND(not a, c), both without key switch; sum + (0,1/8); one key switch
+    rc = bootstrap_woks(ctx, u1, kMU, a_dev, b_dev, 1, 1, -kMU, count, s); if (rc) return rc;
+    rc = bootstrap_woks(ctx, u2, kMU, a_dev, c_dev, -1, 1, -kMU, count, s); if (rc) return rc;
+    CU(launch_lwe_lincomb(u1, u1, u2, 1, 1, kMU, N, count, s));
+    return gate_keyswitch(ctx, result_dev, u1, count, s);
+}
+int tfhe_b200_bootsGate_batch_host(tfhe_b200_ctx* ctx, int op, int32_t* result_host, const int32_t* ca_host, const int32_t* cb_host, int count) {
+    NEED_GATE(); NEED(op >= 0 && op < TFHE_B200_NUM_GATES, "bootsGate: unknown gate");
+    NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_host && ca_host && cb_host), "null buffer");
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)count * (ctx->gp.n + 1) * sizeof(int32_t);
+    int rc = ensure_scratch(ctx, 2, 2 * bytes); if (rc) return rc;
+    rc = ensure_scratch(ctx, 3, bytes); if (rc) return rc;
+    int32_t* da = (int32_t*)ctx->scratch[2]; int32_t* db = da + (size_t)count * (ctx->gp.n + 1); int32_t* dr = (int32_t*)ctx->scratch[3];
+    CU(cudaMemcpyAsync(da, ca_host, bytes, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(db, cb_host, bytes, cudaMemcpyHostToDevice, 0));
+    rc = tfhe_b200_bootsGate_batch(ctx, op, dr, da, db, count, nullptr); if (rc) return rc;
+    CU(cudaMemcpyAsync(result_host, dr, bytes, cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return TFHE_B200_OK;
+}
+
+/* ------------------------------------------------------------------ standalone transforms */
+static const cplx* tw_for(const tfhe_b200_ctx* ctx, int N) { return N == 1024 ? ctx->tw1024 : (N == 2048 ? ctx->tw2048 : nullptr); }
+
+int tfhe_b200_IntPolynomial_ifft_batch(tfhe_b200_ctx* ctx, double* result_dev, const int32_t* poly_dev, int N, int count, void* stream) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(tw_for(ctx, N), "transform: N must be 1024 or 2048"); NEED(count >= 0, "count < 0");
+    CU(launch_poly_to_spectrum32((cplx*)result_dev, poly_dev, tw_for(ctx, N), N, count, 1.0, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_TorusPolynomial64_ifft_batch(tfhe_b200_ctx* ctx, double* result_dev, const int64_t* poly_dev, int N, int count, void* stream) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(tw_for(ctx, N), "transform: N must be 1024 or 2048"); NEED(count >= 0, "count < 0");
+    CU(launch_poly_to_spectrum64((cplx*)result_dev, poly_dev, tw_for(ctx, N), N, count, 1.0, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_TorusPolynomial_fft_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const double* lagr_dev, int N, int count, void* stream) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(tw_for(ctx, N), "transform: N must be 1024 or 2048"); NEED(count >= 0, "count < 0");
+    CU(launch_spectrum_to_torus32(result_dev, (const cplx*)lagr_dev, tw_for(ctx, N), N, count, 2.0 / N, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_TorusPolynomial64_fft_batch(tfhe_b200_ctx* ctx, int64_t* result_dev, const double* lagr_dev, int N, int count, void* stream) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(tw_for(ctx, N), "transform: N must be 1024 or 2048"); NEED(count >= 0, "count < 0");
+    CU(launch_spectrum_to_torus64(result_dev, (const cplx*)lagr_dev, tw_for(ctx, N), N, count, 2.0 / N, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_LagrangeHalfCPolynomialAddMul_batch(tfhe_b200_ctx* ctx, double* res_dev, const double* a_dev, const double* b_dev, int N, int count, void* stream) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(N > 0 && N % 2 == 0 && count >= 0, "AddMul: bad sizes");
+    CU(launch_spectrum_addmul((cplx*)res_dev, (const cplx*)a_dev, (const cplx*)b_dev, (size_t)count * (N / 2), (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+
+/* ------------------------------------------------------------------ circuit bootstrapping */
+static size_t pad512(size_t c) { return (c + 511) / 512 * 512; }
+
+int tfhe_b200_cb_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p, const int32_t* preKS_host, const int64_t* bk_host,
+                           const int32_t* privKS_host) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(p && preKS_host && bk_host, "cb_load_keys: null pointer");
+    NEED(p->N_lvl2 == 2048, "cb params: only N_lvl2 = 2048 is compiled");
+    NEED(p->N_lvl1 == 1024, "cb params: only N_lvl1 = 1024 is compiled");
+    NEED(p->n_lvl0 >= 1 && p->n_lvl0 < 1024, "cb params: n_lvl0 out of range");
+    NEED(p->ell_lvl2 >= 1 && p->ell_lvl2 * p->bgbit_lvl2 < 64 && p->bgbit_lvl2 <= 16, "cb params: bad lvl2 gadget");
+    NEED(p->ell_lvl1 >= 1 && p->ell_lvl1 <= 4 && p->ell_lvl1 * p->bgbit_lvl1 <= 32, "cb params: bad lvl1 gadget");
+    NEED(p->ksbasebit_lvl10 >= 1 && p->ksbasebit_lvl10 <= 3 && p->ksbasebit_lvl21 >= 1 && p->ksbasebit_lvl21 <= 3, "cb params: ks basebit must be 1..3");
+    NEED(p->kslength_lvl10 * p->ksbasebit_lvl10 <= 31 && p->kslength_lvl21 * p->ksbasebit_lvl21 <= 63, "cb params: ks length too large");
+    CU(cudaSetDevice(ctx->device));
+    ctx->cb_ready = false;
+    cudaFree(ctx->c_bkfft); cudaFree(ctx->c_preks); cudaFree(ctx->c_privks);
+    ctx->c_bkfft = nullptr; ctx->c_preks = nullptr; ctx->c_privks = nullptr;
+    ctx->cp = *p;
+    const int N2 = p->N_lvl2, N1 = p->N_lvl1, n0 = p->n_lvl0;
+    // bk (Torus64 coefficients) -> spectra scaled by 2/N   (cb/poc_CircuitBootstrapping.cpp:394-402)
+    {
+        const size_t npoly = (size_t)n0 * 2 * p->ell_lvl2 * 2;
+        int64_t* tmp = nullptr;
+        CU(cudaMalloc(&ctx->c_bkfft, npoly * (N2 / 2) * sizeof(cplx)));
+        CU(cudaMalloc(&tmp, npoly * N2 * sizeof(int64_t)));
+        CU(cudaMemcpy(tmp, bk_host, npoly * N2 * sizeof(int64_t), cudaMemcpyHostToDevice));
+        cudaError_t e = launch_poly_to_spectrum64(ctx->c_bkfft, tmp, ctx->tw2048, N2, (int)npoly, 2.0 / N2, 0);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        cudaFree(tmp);
+        CU(e);
+    }
+    {   // preKS [N1][t10][base10][n0+1]
+        const int base = 1 << p->ksbasebit_lvl10, t = p->kslength_lvl10;
+        const size_t raw = (size_t)N1 * t * base * (n0 + 1), cp = pad512(n0 + 1);
+        int32_t* tmp = nullptr;
+        CU(cudaMalloc(&ctx->c_preks, (size_t)N1 * t * (base - 1) * cp * sizeof(int32_t)));
+        CU(cudaMalloc(&tmp, raw * sizeof(int32_t)));
+        CU(cudaMemcpy(tmp, preKS_host, raw * sizeof(int32_t), cudaMemcpyHostToDevice));
+        cudaError_t e = launch_ks_repack(ctx->c_preks, tmp, N1, t, base, n0 + 1, (int)cp, 0);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        cudaFree(tmp);
+        CU(e);
+    }
+    if (privKS_host) {   // privKS [2][N2+1][t21][base21][2][N1]
+        const int base = 1 << p->ksbasebit_lvl21, t = p->kslength_lvl21, cols = 2 * N1;
+        const size_t raw_u = (size_t)(N2 + 1) * t * base * cols;
+        ctx->c_privks_u_stride = (size_t)(N2 + 1) * t * (base - 1) * cols;
+        int32_t* tmp = nullptr;
+        CU(cudaMalloc(&ctx->c_privks, 2 * ctx->c_privks_u_stride * sizeof(int32_t)));
+        CU(cudaMalloc(&tmp, raw_u * sizeof(int32_t)));
+        for (int u = 0; u < 2; u++) {
+            CU(cudaMemcpy(tmp, privKS_host + (size_t)u * raw_u, raw_u * sizeof(int32_t), cudaMemcpyHostToDevice));
+            cudaError_t e = launch_ks_repack(ctx->c_privks + (size_t)u * ctx->c_privks_u_stride, tmp, N2 + 1, t, base, cols, cols, 0);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { cudaFree(tmp); CU(e); }
+        }
+        cudaFree(tmp);
+    }
+    ctx->cb_ready = true;
+    return TFHE_B200_OK;
+}
+#define NEED_CB() do { if (!ctx) return TFHE_B200_ERR_PARAM; if (!ctx->cb_ready) return fail(ctx, TFHE_B200_ERR_NOKEY, "circuit-bootstrap keys not loaded"); } while (0)
+
+int tfhe_b200_preKeySwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* x_dev, int count, void* stream) {
+    NEED_CB(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && x_dev), "null buffer");
+    const tfhe_b200_cb_params& p = ctx->cp;
+    KSArgs k{};
+    k.in = x_dev; k.in_stride = p.N_lvl1 + 1; k.rows_in = p.N_lvl1; k.t = p.kslength_lvl10; k.basebit = p.ksbasebit_lvl10;
+    k.key = ctx->c_preks; k.cols = p.n_lvl0 + 1; k.cols_pad = (int)pad512(p.n_lvl0 + 1);
+    k.b_col = p.n_lvl0; k.b_index = p.N_lvl1; k.out = result_dev; k.out_stride = p.n_lvl0 + 1; k.count = count;
+    CU(launch_keyswitch32(k, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_preModSwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* x_dev, int count, void* stream) {
+    NEED_CB(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && x_dev), "null buffer");
+    CU(launch_modswitch(result_dev, x_dev, 12 /* 2*N2 = 4096 */, (size_t)count * (ctx->cp.n_lvl0 + 1), (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+static int cb_woks(tfhe_b200_ctx* ctx, int64_t* result_dev, int64_t mu, int n_mu, int mu_bgbit, const int32_t* abar_dev, int count, cudaStream_t s) {
+    const tfhe_b200_cb_params& p = ctx->cp;
+    BRArgs a{};
+    a.bkfft = ctx->c_bkfft; a.tw = ctx->tw2048; a.n = p.n_lvl0; a.l = p.ell_lvl2; a.Bgbit = p.bgbit_lvl2; a.count = count;
+    a.mode = BR_LWE; a.bara = abar_dev; a.mu = mu; a.n_mu = n_mu; a.mu_bgbit = mu_bgbit; a.out = result_dev; a.out_stride = p.N_lvl2 + 1;
+    CU(launch_blind_rotate64(a, s));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_circuitBootstrapWoKS_batch(tfhe_b200_ctx* ctx, int64_t* result_dev, int64_t mu, const int32_t* abar_dev, int count, void* stream) {
+    NEED_CB(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && abar_dev), "null buffer");
+    return cb_woks(ctx, result_dev, mu, 1, 0, abar_dev, count, (cudaStream_t)stream);
+}
+static int cb_privks(tfhe_b200_ctx* ctx, int32_t* result_dev, int out_stride, int u, const int64_t* x_dev, int in_stride, int count, cudaStream_t s) {
+    const tfhe_b200_cb_params& p = ctx->cp;
+    KSArgs k{};
+    k.in = x_dev; k.in_stride = in_stride; k.rows_in = p.N_lvl2 + 1; k.t = p.kslength_lvl21; k.basebit = p.ksbasebit_lvl21;
+    k.key = ctx->c_privks + (size_t)u * ctx->c_privks_u_stride; k.cols = 2 * p.N_lvl1; k.cols_pad = 2 * p.N_lvl1;
+    k.b_col = -1; k.b_index = 0; k.out = result_dev; k.out_stride = out_stride; k.count = count;
+    CU(launch_keyswitch64(k, s));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_circuitPrivKS_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, int u, const int64_t* x_dev, int count, void* stream) {
+    NEED_CB(); NEED(ctx->c_privks, "circuitPrivKS: private key-switch key was not loaded");
+    NEED(u == 0 || u == 1, "circuitPrivKS: u must be 0 or 1"); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && x_dev), "null buffer");
+    return cb_privks(ctx, result_dev, 2 * ctx->cp.N_lvl1, u, x_dev, ctx->cp.N_lvl2 + 1, count, (cudaStream_t)stream);
+}
+int tfhe_b200_CircuitBootstrapFFT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* sample_dev, int count, void* stream) {
+    NEED_CB(); NEED(ctx->c_privks, "CircuitBootstrapFFT: private key-switch key was not loaded");
+    NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && sample_dev), "null buffer");
+    const tfhe_b200_cb_params& p = ctx->cp;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int ell1 = p.ell_lvl1, n0 = p.n_lvl0, N1 = p.N_lvl1, N2 = p.N_lvl2;
+    int rc;
+    if ((rc = ensure_scratch(ctx, 0, (size_t)count * (n0 + 1) * sizeof(int32_t)))) return rc;
+    if ((rc = ensure_scratch(ctx, 1, (size_t)count * (n0 + 1) * sizeof(int32_t)))) return rc;
+    if ((rc = ensure_scratch(ctx, 2, (size_t)count * ell1 * (N2 + 1) * sizeof(int64_t)))) return rc;
+    int32_t* pre = (int32_t*)ctx->scratch[0]; int32_t* abar = (int32_t*)ctx->scratch[1]; int64_t* boot = (int64_t*)ctx->scratch[2];
+    if ((rc = tfhe_b200_preKeySwitch_batch(ctx, pre, sample_dev, count, stream))) return rc;          // :832
+    if ((rc = tfhe_b200_preModSwitch_batch(ctx, abar, pre, count, stream))) return rc;                // :836
+    // both mu_w in one pass over bk: boot[B][ell1][N2+1]                                             // :845-847
+    if ((rc = cb_woks(ctx, boot, 0, ell1, p.bgbit_lvl1, abar, count, s))) return rc;
+    // result[B][u][w][2][N1]: one private key switch per (u,w) over the whole batch                  // :852-855
+    for (int u = 0; u < 2; u++)
+        for (int w = 0; w < ell1; w++) {
+            int32_t* out = result_dev + ((size_t)(u * ell1 + w) * 2) * N1;
+            if ((rc = cb_privks(ctx, out, 2 * ell1 * 2 * N1, u, boot + (size_t)w * (N2 + 1), ell1 * (N2 + 1), count, s))) return rc;
+        }
+    return TFHE_B200_OK;
+}
+int tfhe_b200_CircuitBootstrapFFT_batch_host(tfhe_b200_ctx* ctx, int32_t* result_host, const int32_t* sample_host, int count) {
+    NEED_CB(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_host && sample_host), "null buffer");
+    const tfhe_b200_cb_params& p = ctx->cp;
+    const size_t in_bytes = (size_t)count * (p.N_lvl1 + 1) * sizeof(int32_t);
+    const size_t out_bytes = (size_t)count * 2 * p.ell_lvl1 * 2 * p.N_lvl1 * sizeof(int32_t);
+    int rc = ensure_scratch(ctx, 3, in_bytes + out_bytes); if (rc) return rc;
+    int32_t* din = (int32_t*)ctx->scratch[3]; int32_t* dout = (int32_t*)((char*)ctx->scratch[3] + in_bytes);
+    CU(cudaMemcpyAsync(din, sample_host, in_bytes, cudaMemcpyHostToDevice, 0));
+    rc = tfhe_b200_CircuitBootstrapFFT_batch(ctx, dout, din, count, nullptr); if (rc) return rc;
+    CU(cudaMemcpyAsync(result_host, dout, out_bytes, cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return TFHE_B200_OK;
+}
+
+/* ------------------------------------------------------------------ high-precision FFT */
+static int hp_tables(tfhe_b200_ctx* ctx, int N, const uint64_t** om, const uint64_t** ob) {
+    NEED(N == 2048 || N == 4096, "hp FFT: N must be 2048 or 4096");
+    const int slot = N == 2048 ? 0 : 1;
+    if (!ctx->hp_omega[slot]) {
+        const int n = 2 * N;
+        std::vector<uint64_t> h((size_t)4 * n);
+        for (int inv = 0; inv < 2; inv++) {
+            make_hp_tables(n, inv, h.data());
+            uint64_t** dst = inv ? &ctx->hp_ombar[slot] : &ctx->hp_omega[slot];
+            CU(cudaMalloc(dst, h.size() * sizeof(uint64_t)));
+            CU(cudaMemcpy(*dst, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        }
+    }
+    *om = ctx->hp_omega[slot]; *ob = ctx->hp_ombar[slot];
+    return TFHE_B200_OK;
+}
+int tfhe_b200_hp_iFFT_batch(tfhe_b200_ctx* ctx, tfhe_b200_cplx96* out_dev, const int64_t* in_dev, int N, int count, void* stream) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    const uint64_t *om, *ob; int rc = hp_tables(ctx, N, &om, &ob); if (rc) return rc;
+    NEED(count >= 0, "count < 0"); NEED(count == 0 || (out_dev && in_dev), "null buffer");
+    CU(launch_hp_ifft(out_dev, in_dev, om, N, count, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_hp_FFT_batch(tfhe_b200_ctx* ctx, int64_t* out_dev, const tfhe_b200_cplx96* in_dev, int N, int count, void* stream) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    const uint64_t *om, *ob; int rc = hp_tables(ctx, N, &om, &ob); if (rc) return rc;
+    NEED(count >= 0, "count < 0"); NEED(count == 0 || (out_dev && in_dev), "null buffer");
+    CU(launch_hp_fft(out_dev, in_dev, ob, N, count, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

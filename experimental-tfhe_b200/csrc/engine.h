@@ -1,0 +1,82 @@
+// engine.h -- internal C++ interface between the C-ABI layer (capi.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/tfhe_b200.h"
+
+namespace tfhe_b200 {
+
+typedef double2 cplx;
+
+// host-side twiddle generation (twiddles.cpp): FftPlan<LOGM> layout, entries are (re,im) pairs
+void make_fft_tables(int logM, double* out /* 2 * TW_TOTAL doubles */);
+int  fft_table_entries(int logM);
+// hp tables: 2N entries of {re_lo,re_hi,im_lo,im_hi}; inverse=0 -> powomega, 1 -> powombar (hp/code.cpp:378-388)
+void make_hp_tables(int n2N, int inverse, uint64_t* out /* 4 * n2N words */);
+
+// ------------------------------------------------------------------ blind rotation (br_kernels.cu)
+enum BRMode { BR_ACCUM = 0, BR_TESTVEC = 1, BR_LWE = 2 };
+struct BRArgs {
+    const cplx* bkfft;    // [n][2l][2][M] spectra, pre-scaled by 2/N
+    const cplx* tw;       // FftPlan table
+    int n, l, Bgbit, count, mode;
+    // BR_ACCUM  : accum[B][2][N] in/out, bara[B][n]
+    // BR_TESTVEC: v[N], barb[B], bara[B][n] -> out[B][N+1]
+    // BR_LWE    : x = (0,cconst) + ka*xa + kb*xb (LWE(n) samples, xb may be null), test vector = mu -> out[B][N+1]
+    void* accum;
+    const int32_t* bara;
+    const int32_t* barb;
+    const void* v;
+    const int32_t* xa;
+    const int32_t* xb;
+    int ka, kb;
+    int32_t cconst;
+    int64_t mu;           // Torus32 path uses the low 32 bits
+    void* out;
+    int out_stride;       // elements between consecutive outputs (N+1 by default)
+    // Torus64 (circuit bootstrap) only: number of test vectors sharing one pass (mu_w = 2^(64-(w+1)*bgbit1))
+    int n_mu; int mu_bgbit;
+};
+cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s);     // N = 1024, Torus32
+cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s);     // N = 2048, Torus64 (circuitBootstrapWoKS)
+cudaError_t blind_rotate_init();                                         // opt-in shared memory sizes
+
+// coefficient polynomials -> spectra in engine order; scale applied to the output
+cudaError_t launch_poly_to_spectrum32(cplx* out, const int32_t* in, const cplx* tw, int N, int count, double scale, cudaStream_t s);
+cudaError_t launch_poly_to_spectrum64(cplx* out, const int64_t* in, const cplx* tw, int N, int count, double scale, cudaStream_t s);
+cudaError_t launch_spectrum_to_torus32(int32_t* out, const cplx* in, const cplx* tw, int N, int count, double scale, cudaStream_t s);
+cudaError_t launch_spectrum_to_torus64(int64_t* out, const cplx* in, const cplx* tw, int N, int count, double scale, cudaStream_t s);
+cudaError_t launch_spectrum_addmul(cplx* res, const cplx* a, const cplx* b, size_t n_cplx, cudaStream_t s);
+
+// ------------------------------------------------------------------ key switching (ks_kernels.cu)
+// Device key layout: int32 [rows_in][t][base-1][cols_pad], cols_pad multiple of 512 (d = 0 rows dropped).
+struct KSArgs {
+    const void* in;        // [B][in_stride] torus (32 or 64 bit)
+    int in_stride;         // elements per input sample
+    int rows_in;           // number of input coefficients consumed (N, or N2+1 for the private KS)
+    int t, basebit;
+    const int32_t* key;    // device layout above
+    int cols, cols_pad;    // output width (n+1, or 2*N1)
+    int b_col;             // >= 0: out[b_col] starts at (int32) in[b_index]; < 0: starts at 0
+    int b_index;
+    int32_t* out;          // [B][out_stride]
+    int out_stride;
+    int count;
+};
+cudaError_t launch_keyswitch32(const KSArgs& a, cudaStream_t s);
+cudaError_t launch_keyswitch64(const KSArgs& a, cudaStream_t s);
+// raw [rows][t][base][cols] -> device layout
+cudaError_t launch_ks_repack(int32_t* dst, const int32_t* src, int rows, int t, int base, int cols, int cols_pad, cudaStream_t s);
+
+// ------------------------------------------------------------------ small elementwise (misc_kernels.cu)
+cudaError_t launch_lwe_lincomb(int32_t* out, const int32_t* a, const int32_t* b, int ka, int kb, int32_t cconst,
+                               int n, int count, cudaStream_t s);   // out = (0,cconst) + ka*a + kb*b   (b may be null)
+cudaError_t launch_modswitch(int32_t* out, const int32_t* in, int Msize_log2, size_t total, cudaStream_t s);
+
+// ------------------------------------------------------------------ high-precision FFT (hp_kernels.cu)
+cudaError_t launch_hp_ifft(tfhe_b200_cplx96* out, const int64_t* in, const uint64_t* powomega, int N, int count, cudaStream_t s);
+cudaError_t launch_hp_fft(int64_t* out, const tfhe_b200_cplx96* in, const uint64_t* powombar, int N, int count, cudaStream_t s);
+cudaError_t hp_init();
+
+}  // namespace tfhe_b200

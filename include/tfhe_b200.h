@@ -1,0 +1,181 @@
+/*
+ * tfhe_b200.h -- C ABI of the B200-native TFHE bootstrapping engine.
+ *
+ * Drop-in boundary for the hot path of tfhe/experimental-tfhe.  Every entry point
+ * names the reference function it replaces; "cb/" = circuit-bootstrapping/src/, "hp/" =
+ * high-precision-anticyclic-fft/src/ of the reference tree.  The reference processes ONE sample per
+ * call on host structs made of separately allocated polynomials (cb/poc_types.h:137-251); this ABI
+ * processes a BATCH of samples held in flat, contiguous arrays:
+ *
+ *   LWE sample, dimension n      : torus[n+1]            a[0..n) then b          (cb/poc_types.h:137-158)
+ *   TLWE sample, degree N, k=1   : torus[2][N]           a polynomial then b     (cb/poc_types.h:164-184)
+ *   TGSW sample                  : torus[2*l][2][N]      row p = bloc*l + i      (cb/poc_types.h:206-234)
+ *   bootstrapping key            : TGSW[n], COEFFICIENT domain (transformed on the device at load)
+ *   LWE key-switching key        : int32[N_in][t][base][n_out+1]                 (cb/lwe_functions.cpp:96-110)
+ *   private key-switching key    : int32[2][n_in+1][t][base][2][N_out]           (cb/poc_CircuitBootstrapping.cpp:408)
+ *   batches                      : sample index is the slowest dimension.
+ *
+ * Pointers named *_dev are device pointers on the context's GPU; *_host are host pointers (pinned
+ * memory gives full PCIe speed but is not required).  `stream` is a cudaStream_t passed as void*
+ * (NULL = the legacy default stream).  All *_batch calls on device pointers are asynchronous on
+ * `stream`; *_host calls return after the results are in host memory.
+ *
+ * Errors: the reference has none (assert/abort).  Here every call returns TFHE_B200_OK or a negative
+ * code and tfhe_b200_last_error() gives the message.  There is NO CPU fallback: without a usable
+ * sm_100 device tfhe_b200_ctx_create fails.
+ */
+#ifndef TFHE_B200_H
+#define TFHE_B200_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFHE_B200_OK            0
+#define TFHE_B200_ERR_CUDA     -1   /* CUDA runtime error (message has the cudaError string) */
+#define TFHE_B200_ERR_PARAM    -2   /* unsupported / inconsistent parameter set or argument */
+#define TFHE_B200_ERR_NOKEY    -3   /* key material for this call has not been loaded */
+#define TFHE_B200_ERR_NODEVICE -4   /* no CUDA device of compute capability 10.x */
+
+typedef struct tfhe_b200_ctx tfhe_b200_ctx;
+
+/* One context per process and GPU; owns key storage and scratch (reference: none -- keys live in
+ * `Globals`, cb/poc_types.h:267-312, temporaries are new/delete'd per call, cb/poc_CircuitBootstrapping.cpp:537-546). */
+int         tfhe_b200_ctx_create(tfhe_b200_ctx** ctx, int device_ordinal);
+int         tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx);
+const char* tfhe_b200_last_error(const tfhe_b200_ctx* ctx);   /* ctx may be NULL: last create error */
+int         tfhe_b200_sm_count(const tfhe_b200_ctx* ctx);
+int         tfhe_b200_synchronize(tfhe_b200_ctx* ctx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gate bootstrapping, 32-bit torus (library-style path, cb/lwe_functions.cpp + cb/tgsw_functions.cpp)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n;          /* LweParams::n                         cb/lwe_functions.cpp:17   */
+    int32_t N;          /* TLweParams::N (1024)                 cb/tlwe_functions.cpp:14  */
+    int32_t k;          /* TLweParams::k, must be 1             cb/poc_types.h:10         */
+    int32_t bk_l;       /* TGswParams::l                        cb/tgsw_functions.cpp:15  */
+    int32_t bk_Bgbit;   /* TGswParams::Bgbit                    cb/tgsw_functions.cpp:15  */
+    int32_t ks_t;       /* LweKeySwitchKey::t                   cb/lwe_functions.cpp:96   */
+    int32_t ks_basebit; /* LweKeySwitchKey::basebit             cb/lwe_functions.cpp:96   */
+} tfhe_b200_gate_params;
+
+/* Replaces init_LweBootstrappingKeyFFT (cb/lwe_functions.cpp:287-316): takes the coefficient-domain
+ * bootstrapping key bk[n][2l][2][N] and the key-switching key ks[N][t][base][n+1] from HOST memory,
+ * transforms bk on the device (tGswToFFTConvert, cb/tgsw_functions.cpp:389-394) into the engine's
+ * private spectral layout and repacks ks for coalesced reads. */
+int tfhe_b200_gate_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p,
+                             const int32_t* bk_host, const int32_t* ks_host);
+/* Multi-GPU replication: rank 0 loads keys, every other rank allocates, then the two
+ * device blobs are broadcast (NCCL / cudaMemcpyPeer) by the caller.  which: 0 = bk spectra, 1 = ks. */
+int tfhe_b200_gate_alloc_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p);
+int tfhe_b200_gate_key_blob(tfhe_b200_ctx* ctx, int which, void** dev_ptr, size_t* bytes);
+
+/* tfhe_blindRotate_FFT (cb/lwe_functions.cpp:337-361): accum[B][2][N] in/out, bara[B][n] in [0,2N). */
+int tfhe_b200_blindRotate_FFT_batch(tfhe_b200_ctx* ctx, int32_t* accum_dev, const int32_t* bara_dev,
+                                    int count, void* stream);
+/* tfhe_blindRotateAndExtract_FFT (cb/lwe_functions.cpp:366-395): result[B][N+1]; v[N] one test
+ * polynomial shared by the batch; barb[B]; bara[B][n]. */
+int tfhe_b200_blindRotateAndExtract_FFT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* v_dev,
+                                              const int32_t* barb_dev, const int32_t* bara_dev,
+                                              int count, void* stream);
+/* tfhe_bootstrap_woKS_FFT (cb/lwe_functions.cpp:399-430): result[B][N+1], x[B][n+1]. */
+int tfhe_b200_bootstrap_woKS_FFT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, int32_t mu,
+                                       const int32_t* x_dev, int count, void* stream);
+/* lweKeySwitch (cb/lwe_functions.cpp:163-171): result[B][n+1], sample[B][N+1]. */
+int tfhe_b200_lweKeySwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* sample_dev,
+                                 int count, void* stream);
+/* tfhe_bootstrap_FFT (cb/lwe_functions.cpp:434-446): result[B][n+1], x[B][n+1]. */
+int tfhe_b200_bootstrap_FFT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, int32_t mu,
+                                  const int32_t* x_dev, int count, void* stream);
+
+/* boots* gates (upstream tfhe/tfhe boot-gates.cpp -- not in the reference tree; semantics in
+ * SURVEY.md Appendix C): tmp = (0,c) + ka*ca + kb*cb, then tfhe_bootstrap_FFT(result, bk, 1/8, tmp). */
+enum {
+    TFHE_B200_NAND = 0, TFHE_B200_AND, TFHE_B200_OR, TFHE_B200_NOR, TFHE_B200_XOR, TFHE_B200_XNOR,
+    TFHE_B200_ANDNY, TFHE_B200_ANDYN, TFHE_B200_ORNY, TFHE_B200_ORYN, TFHE_B200_NUM_GATES
+};
+int tfhe_b200_bootsGate_batch(tfhe_b200_ctx* ctx, int op, int32_t* result_dev, const int32_t* ca_dev,
+                              const int32_t* cb_dev, int count, void* stream);
+/* bootsNOT: negation, no bootstrapping. */
+int tfhe_b200_bootsNOT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* ca_dev, int count, void* stream);
+/* bootsMUX(a,b,c) = a ? b : c : two bootstraps without key switch, one key switch. */
+int tfhe_b200_bootsMUX_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* a_dev, const int32_t* b_dev,
+                             const int32_t* c_dev, int count, void* stream);
+/* Same gate call on HOST buffers: H2D of ca/cb, the gate, D2H of result, all inside the call
+ * (this is the end-to-end path a reference user would bind). */
+int tfhe_b200_bootsGate_batch_host(tfhe_b200_ctx* ctx, int op, int32_t* result_host, const int32_t* ca_host,
+                                   const int32_t* cb_host, int count);
+
+/* ------------------------------------------------------------------------------------------------
+ * Negacyclic FP64 transforms (cb/spqlios/fft_processor_spqlios.cpp).  The spectral ("LagrangeHalfC")
+ * layout is engine-private, exactly as the reference's is private to spqlios: N doubles per
+ * polynomial, only meaningful to these functions.  Pointwise products are order-agnostic.
+ * N in {1024, 2048}.
+ * ---------------------------------------------------------------------------------------------- */
+/* IntPolynomial_ifft / execute_reverse_int (:27-67) */
+int tfhe_b200_IntPolynomial_ifft_batch(tfhe_b200_ctx* ctx, double* result_dev, const int32_t* poly_dev,
+                                       int N, int count, void* stream);
+/* TorusPolynomial64_ifft_lvl2 / execute_reverse_torus64 (:166-170) */
+int tfhe_b200_TorusPolynomial64_ifft_batch(tfhe_b200_ctx* ctx, double* result_dev, const int64_t* poly_dev,
+                                           int N, int count, void* stream);
+/* TorusPolynomial_fft / execute_direct_torus32 (:77-103): scales by 2/N, truncates int32(int64(x)). */
+int tfhe_b200_TorusPolynomial_fft_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const double* lagr_dev,
+                                        int N, int count, void* stream);
+/* TorusPolynomial64_fft_lvl2 / execute_direct_torus64 (:105-156) */
+int tfhe_b200_TorusPolynomial64_fft_batch(tfhe_b200_ctx* ctx, int64_t* result_dev, const double* lagr_dev,
+                                          int N, int count, void* stream);
+/* LagrangeHalfCPolynomialAddMul (cb/spqlios/lagrangehalfc_impl_fma.s:78-135): res += a (.) b */
+int tfhe_b200_LagrangeHalfCPolynomialAddMul_batch(tfhe_b200_ctx* ctx, double* res_dev, const double* a_dev,
+                                                  const double* b_dev, int N, int count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Circuit bootstrapping (cb/poc_CircuitBootstrapping.cpp), LWE32(N1) -> TRGSW32(N1)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_lvl0, N_lvl1, N_lvl2;               /* :71-73 */
+    int32_t bgbit_lvl1, ell_lvl1;                 /* :74-75 */
+    int32_t bgbit_lvl2, ell_lvl2;                 /* :76-77 */
+    int32_t kslength_lvl10, ksbasebit_lvl10;      /* :80-81 */
+    int32_t kslength_lvl21, ksbasebit_lvl21;      /* :83-84 */
+} tfhe_b200_cb_params;
+
+/* Replaces the cloud-key part of Globals::Globals (:372-419).  preKS[N1][t10][base10][n0+1],
+ * bk[n0][2*l2][2][N2] (Torus64, coefficient domain), privKS[2][N2+1][t21][base21][2][N1] or NULL. */
+int tfhe_b200_cb_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p, const int32_t* preKS_host,
+                           const int64_t* bk_host, const int32_t* privKS_host);
+/* preKeySwitch (:437-465): result[B][n0+1], x[B][N1+1] */
+int tfhe_b200_preKeySwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* x_dev, int count, void* stream);
+/* preModSwitch (:472-484): result[B][n0+1] in [0, 2*N2) */
+int tfhe_b200_preModSwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* x_dev, int count, void* stream);
+/* circuitBootstrapWoKS (:530-659, with the corrections D1-D3 of SURVEY Appendix B):
+ * result[B][N2+1] (Torus64), abar[B][n0+1]. */
+int tfhe_b200_circuitBootstrapWoKS_batch(tfhe_b200_ctx* ctx, int64_t* result_dev, int64_t mu,
+                                         const int32_t* abar_dev, int count, void* stream);
+/* circuitPrivKS (:667-698): result[B][2][N1], x[B][N2+1] */
+int tfhe_b200_circuitPrivKS_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, int u, const int64_t* x_dev,
+                                  int count, void* stream);
+/* tfhe_CircuitBootstrapFFT (:823-873): result[B][2][l1][2][N1] (= samples[u][w]), sample[B][N1+1] */
+int tfhe_b200_CircuitBootstrapFFT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* sample_dev,
+                                        int count, void* stream);
+int tfhe_b200_CircuitBootstrapFFT_batch_host(tfhe_b200_ctx* ctx, int32_t* result_host, const int32_t* sample_host,
+                                             int count);
+
+/* ------------------------------------------------------------------------------------------------
+ * High-precision anticyclic FFT, 128-bit fixed point (hp/code.cpp).  Real96 = value * 2^64 in a
+ * wrapping 128-bit integer stored as {lo, hi} 64-bit words (little endian, == unsigned __int128).
+ * Complex = {re, im}.  N in {2048, 4096}.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { uint64_t re_lo, re_hi, im_lo, im_hi; } tfhe_b200_cplx96;
+/* iFFT (hp/code.cpp:391-443): out[B][N/2], in[B][N] */
+int tfhe_b200_hp_iFFT_batch(tfhe_b200_ctx* ctx, tfhe_b200_cplx96* out_dev, const int64_t* in_dev,
+                            int N, int count, void* stream);
+/* FFT (hp/code.cpp:446-512): out[B][N], in[B][N/2] (not clobbered, unlike the reference) */
+int tfhe_b200_hp_FFT_batch(tfhe_b200_ctx* ctx, int64_t* out_dev, const tfhe_b200_cplx96* in_dev,
+                           int N, int count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFHE_B200_H */

@@ -1,0 +1,34 @@
+"""GPU parity for the 128-bit fixed-point anticyclic FFT (hp/code.cpp): exact integer arithmetic -> bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("N", [2048, 4096])
+def test_hp_fft_bit_exact(engine, N):
+    rng = np.random.default_rng(46)
+    B = 4
+    inp = rng.integers(-2**63, 2**63 - 1, size=(B, N), dtype=np.int64)
+    inp[1, :] = 0
+    inp[2, :8] = [2**63 - 1, -2**63, -1, 1, 0, 2**62, -2**62, 12345]
+    om, ob = O.hp_tables(N)
+    d_in = torch.from_numpy(inp).to(DEV)
+    spec = torch.empty((B, N // 2, 4), dtype=torch.int64, device=DEV)
+    back = torch.empty((B, N), dtype=torch.int64, device=DEV)
+    engine.hp_iFFT(spec, d_in, N, B)
+    engine.hp_FFT(back, spec, N, B)
+    torch.cuda.synchronize()
+    spec_h = spec.cpu().numpy().view(np.uint64)
+    back_h = back.cpu().numpy()
+    for b in range(B):
+        ref_spec = O.hp_iFFT(inp[b], N, om)
+        assert np.array_equal(spec_h[b], ref_spec), f"iFFT differs for polynomial {b}"
+        ref_back = O.hp_FFT(ref_spec, N, ob)
+        assert np.array_equal(back_h[b], ref_back), f"FFT differs for polynomial {b}"
+        # the reference's own bar: round trip == input up to a few LSB (hp/code.cpp:582-583 prints revout^in)
+        assert np.abs((back_h[b] - inp[b]).astype(np.int64)).max() <= 16
