@@ -83,6 +83,10 @@ _SIGS = {
     "tfhe_b200_CircuitBootstrapFFT_batch_host": [_P, _P, _P, _I],
     "tfhe_b200_hp_iFFT_batch": [_P, _P, _P, _I, _I, _P],
     "tfhe_b200_hp_FFT_batch": [_P, _P, _P, _I, _I, _P],
+    "tfhe_b200_profile_enable": [_P, _I],
+    "tfhe_b200_profile_read": [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)],
+    "tfhe_b200_probe_fp64_tflops": [_P, ctypes.POINTER(ctypes.c_double)],
+    "tfhe_b200_probe_read_gbs": [_P, ctypes.c_size_t, _I, ctypes.POINTER(ctypes.c_double)],
 }
 EXPORTS = sorted(list(_SIGS) + ["tfhe_b200_last_error"])
 
@@ -160,6 +164,27 @@ class Engine:
 
     def synchronize(self, stream=None):
         self._ck(self.lib.tfhe_b200_synchronize(self.h, self._stream(stream)), "synchronize")
+
+    # ------------------------------------------------------------------ diagnostics
+    def profile_enable(self, on=True):
+        self._ck(self.lib.tfhe_b200_profile_enable(self.h, int(bool(on))), "profile_enable")
+
+    def profile_read(self):
+        """-> ({'blind_rotate': ms, 'keyswitch': ms, 'other': ms}, {same keys: launches})"""
+        ms = (ctypes.c_double * 3)(); n = (ctypes.c_int * 3)()
+        self._ck(self.lib.tfhe_b200_profile_read(self.h, ms, n), "profile_read")
+        names = ("blind_rotate", "keyswitch", "other")
+        return dict(zip(names, list(ms))), dict(zip(names, list(n)))
+
+    def probe_fp64_tflops(self):
+        v = ctypes.c_double()
+        self._ck(self.lib.tfhe_b200_probe_fp64_tflops(self.h, ctypes.byref(v)), "probe_fp64_tflops")
+        return v.value
+
+    def probe_read_gbs(self, nbytes, passes):
+        v = ctypes.c_double()
+        self._ck(self.lib.tfhe_b200_probe_read_gbs(self.h, nbytes, passes, ctypes.byref(v)), "probe_read_gbs")
+        return v.value
 
     # ------------------------------------------------------------------ gate path
     def load_gate_keys(self, params, bk_host, ks_host):

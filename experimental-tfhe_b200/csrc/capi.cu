@@ -35,6 +35,23 @@ struct tfhe_b200_ctx {
     // scratch (grown on demand, never per call once warm)
     void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[4] = {0, 0, 0, 0};
+    // profiling (diagnostics): events around every launch when enabled
+    bool profiling = false;
+    struct Span { cudaEvent_t a, b; int cat; };
+    std::vector<Span> spans;
+};
+
+// brackets one kernel launch with events on its stream when profiling is on
+struct ProfScope {
+    tfhe_b200_ctx* c; cudaStream_t s; int idx = -1;
+    ProfScope(tfhe_b200_ctx* ctx, int cat, cudaStream_t st) : c(ctx), s(st) {
+        if (!c->profiling) return;
+        tfhe_b200_ctx::Span sp; sp.cat = cat;
+        cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
+        cudaEventRecord(sp.a, s);
+        c->spans.push_back(sp); idx = (int)c->spans.size() - 1;
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(c->spans[idx].b, s); }
 };
 
 static std::string g_create_err;
@@ -210,7 +227,7 @@ int tfhe_b200_blindRotate_FFT_batch(tfhe_b200_ctx* ctx, int32_t* accum_dev, cons
     NEED_GATE(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (accum_dev && bara_dev), "null buffer");
     BRArgs a = gate_br_args(ctx, count);
     a.mode = BR_ACCUM; a.accum = accum_dev; a.bara = bara_dev;
-    CU(launch_blind_rotate32(a, (cudaStream_t)stream));
+    { ProfScope ps(ctx, 0, (cudaStream_t)stream); CU(launch_blind_rotate32(a, (cudaStream_t)stream)); }
     return TFHE_B200_OK;
 }
 int tfhe_b200_blindRotateAndExtract_FFT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* v_dev, const int32_t* barb_dev,
@@ -218,14 +235,14 @@ int tfhe_b200_blindRotateAndExtract_FFT_batch(tfhe_b200_ctx* ctx, int32_t* resul
     NEED_GATE(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && v_dev && barb_dev && bara_dev), "null buffer");
     BRArgs a = gate_br_args(ctx, count);
     a.mode = BR_TESTVEC; a.v = v_dev; a.barb = barb_dev; a.bara = bara_dev; a.out = result_dev;
-    CU(launch_blind_rotate32(a, (cudaStream_t)stream));
+    { ProfScope ps(ctx, 0, (cudaStream_t)stream); CU(launch_blind_rotate32(a, (cudaStream_t)stream)); }
     return TFHE_B200_OK;
 }
 static int bootstrap_woks(tfhe_b200_ctx* ctx, int32_t* result_dev, int32_t mu, const int32_t* xa, const int32_t* xb, int ka, int kb,
                           int32_t cconst, int count, cudaStream_t s) {
     BRArgs a = gate_br_args(ctx, count);
     a.mode = BR_LWE; a.xa = xa; a.xb = xb; a.ka = ka; a.kb = kb; a.cconst = cconst; a.mu = mu; a.out = result_dev;
-    CU(launch_blind_rotate32(a, s));
+    { ProfScope ps(ctx, 0, s); CU(launch_blind_rotate32(a, s)); }
     return TFHE_B200_OK;
 }
 int tfhe_b200_bootstrap_woKS_FFT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, int32_t mu, const int32_t* x_dev, int count, void* stream) {
@@ -237,7 +254,7 @@ static int gate_keyswitch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t
     k.in = sample_dev; k.in_stride = ctx->gp.N + 1; k.rows_in = ctx->gp.N; k.t = ctx->gp.ks_t; k.basebit = ctx->gp.ks_basebit;
     k.key = ctx->g_ks; k.cols = ctx->gp.n + 1; k.cols_pad = (int)gate_cols_pad(ctx->gp);
     k.b_col = ctx->gp.n; k.b_index = ctx->gp.N; k.out = result_dev; k.out_stride = ctx->gp.n + 1; k.count = count;
-    CU(launch_keyswitch32(k, s));
+    { ProfScope ps(ctx, 1, s); CU(launch_keyswitch32(k, s)); }
     return TFHE_B200_OK;
 }
 int tfhe_b200_lweKeySwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* sample_dev, int count, void* stream) {
@@ -271,7 +288,7 @@ int tfhe_b200_bootsGate_batch(tfhe_b200_ctx* ctx, int op, int32_t* result_dev, c
 }
 int tfhe_b200_bootsNOT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* ca_dev, int count, void* stream) {
     NEED_GATE(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && ca_dev), "null buffer");
-    CU(launch_lwe_lincomb(result_dev, ca_dev, nullptr, -1, 0, 0, ctx->gp.n, count, (cudaStream_t)stream));
+    { ProfScope ps(ctx, 2, (cudaStream_t)stream); CU(launch_lwe_lincomb(result_dev, ca_dev, nullptr, -1, 0, 0, ctx->gp.n, count, (cudaStream_t)stream)); }
     return TFHE_B200_OK;
 }
 int tfhe_b200_bootsMUX_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* a_dev, const int32_t* b_dev, const int32_t* c_dev,
@@ -286,7 +303,7 @@ int tfhe_b200_bootsMUX_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int3
     // AND(a,b) and AND(not a, c), both without key switch; sum + (0,1/8); one key switch
     rc = bootstrap_woks(ctx, u1, kMU, a_dev, b_dev, 1, 1, -kMU, count, s); if (rc) return rc;
     rc = bootstrap_woks(ctx, u2, kMU, a_dev, c_dev, -1, 1, -kMU, count, s); if (rc) return rc;
-    CU(launch_lwe_lincomb(u1, u1, u2, 1, 1, kMU, N, count, s));
+    { ProfScope ps(ctx, 2, s); CU(launch_lwe_lincomb(u1, u1, u2, 1, 1, kMU, N, count, s)); }
     return gate_keyswitch(ctx, result_dev, u1, count, s);
 }
 int tfhe_b200_bootsGate_batch_host(tfhe_b200_ctx* ctx, int op, int32_t* result_host, const int32_t* ca_host, const int32_t* cb_host, int count) {
@@ -410,12 +427,12 @@ int tfhe_b200_preKeySwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const 
     k.in = x_dev; k.in_stride = p.N_lvl1 + 1; k.rows_in = p.N_lvl1; k.t = p.kslength_lvl10; k.basebit = p.ksbasebit_lvl10;
     k.key = ctx->c_preks; k.cols = p.n_lvl0 + 1; k.cols_pad = (int)pad512(p.n_lvl0 + 1);
     k.b_col = p.n_lvl0; k.b_index = p.N_lvl1; k.out = result_dev; k.out_stride = p.n_lvl0 + 1; k.count = count;
-    CU(launch_keyswitch32(k, (cudaStream_t)stream));
+    { ProfScope ps(ctx, 1, (cudaStream_t)stream); CU(launch_keyswitch32(k, (cudaStream_t)stream)); }
     return TFHE_B200_OK;
 }
 int tfhe_b200_preModSwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* x_dev, int count, void* stream) {
     NEED_CB(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && x_dev), "null buffer");
-    CU(launch_modswitch(result_dev, x_dev, 12 /* 2*N2 = 4096 */, (size_t)count * (ctx->cp.n_lvl0 + 1), (cudaStream_t)stream));
+    { ProfScope ps(ctx, 2, (cudaStream_t)stream); CU(launch_modswitch(result_dev, x_dev, 12 /* 2*N2 = 4096 */, (size_t)count * (ctx->cp.n_lvl0 + 1), (cudaStream_t)stream)); }
     return TFHE_B200_OK;
 }
 static int cb_woks(tfhe_b200_ctx* ctx, int64_t* result_dev, int64_t mu, int n_mu, int mu_bgbit, const int32_t* abar_dev, int count, cudaStream_t s) {
@@ -423,7 +440,7 @@ static int cb_woks(tfhe_b200_ctx* ctx, int64_t* result_dev, int64_t mu, int n_mu
     BRArgs a{};
     a.bkfft = ctx->c_bkfft; a.tw = ctx->tw2048; a.n = p.n_lvl0; a.l = p.ell_lvl2; a.Bgbit = p.bgbit_lvl2; a.count = count;
     a.mode = BR_LWE; a.bara = abar_dev; a.mu = mu; a.n_mu = n_mu; a.mu_bgbit = mu_bgbit; a.out = result_dev; a.out_stride = p.N_lvl2 + 1;
-    CU(launch_blind_rotate64(a, s));
+    { ProfScope ps(ctx, 0, s); CU(launch_blind_rotate64(a, s)); }
     return TFHE_B200_OK;
 }
 int tfhe_b200_circuitBootstrapWoKS_batch(tfhe_b200_ctx* ctx, int64_t* result_dev, int64_t mu, const int32_t* abar_dev, int count, void* stream) {
@@ -436,7 +453,7 @@ static int cb_privks(tfhe_b200_ctx* ctx, int32_t* result_dev, int out_stride, in
     k.in = x_dev; k.in_stride = in_stride; k.rows_in = p.N_lvl2 + 1; k.t = p.kslength_lvl21; k.basebit = p.ksbasebit_lvl21;
     k.key = ctx->c_privks + (size_t)u * ctx->c_privks_u_stride; k.cols = 2 * p.N_lvl1; k.cols_pad = 2 * p.N_lvl1;
     k.b_col = -1; k.b_index = 0; k.out = result_dev; k.out_stride = out_stride; k.count = count;
-    CU(launch_keyswitch64(k, s));
+    { ProfScope ps(ctx, 1, s); CU(launch_keyswitch64(k, s)); }
     return TFHE_B200_OK;
 }
 int tfhe_b200_circuitPrivKS_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, int u, const int64_t* x_dev, int count, void* stream) {
@@ -510,6 +527,40 @@ int tfhe_b200_hp_FFT_batch(tfhe_b200_ctx* ctx, int64_t* out_dev, const tfhe_b200
     const uint64_t *om, *ob; int rc = hp_tables(ctx, N, &om, &ob); if (rc) return rc;
     NEED(count >= 0, "count < 0"); NEED(count == 0 || (out_dev && in_dev), "null buffer");
     CU(launch_hp_fft(out_dev, in_dev, ob, N, count, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+
+/* ------------------------------------------------------------------ diagnostics */
+int tfhe_b200_profile_enable(tfhe_b200_ctx* ctx, int on) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    ctx->profiling = on != 0;
+    return TFHE_B200_OK;
+}
+int tfhe_b200_profile_read(tfhe_b200_ctx* ctx, double ms[3], int launches[3]) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(ms && launches, "profile_read: null output");
+    for (int i = 0; i < 3; i++) { ms[i] = 0; launches[i] = 0; }
+    for (auto& sp : ctx->spans) {
+        CU(cudaEventSynchronize(sp.b));
+        float t = 0; CU(cudaEventElapsedTime(&t, sp.a, sp.b));
+        ms[sp.cat] += t; launches[sp.cat]++;
+        cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+    }
+    ctx->spans.clear();
+    return TFHE_B200_OK;
+}
+int tfhe_b200_probe_fp64_tflops(tfhe_b200_ctx* ctx, double* tflops) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(tflops, "probe: null output");
+    CU(cudaSetDevice(ctx->device));
+    CU(probe_fp64(tflops));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_probe_read_gbs(tfhe_b200_ctx* ctx, size_t bytes, int passes, double* gbs) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(gbs && bytes >= 4096 && passes >= 1, "probe: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    CU(probe_read(bytes, passes, gbs));
     return TFHE_B200_OK;
 }
 

@@ -72,6 +72,8 @@ cudaError_t launch_ks_repack(int32_t* dst, const int32_t* src, int rows, int t, 
 // ------------------------------------------------------------------ small elementwise (misc_kernels.cu)
 cudaError_t launch_lwe_lincomb(int32_t* out, const int32_t* a, const int32_t* b, int ka, int kb, int32_t cconst,
                                int n, int count, cudaStream_t s);   // out = (0,cconst) + ka*a + kb*b   (b may be null)
+cudaError_t probe_fp64(double* tflops);
+cudaError_t probe_read(size_t bytes, int passes, double* gbs);
 cudaError_t launch_modswitch(int32_t* out, const int32_t* in, int Msize_log2, size_t total, cudaStream_t s);
 
 // ------------------------------------------------------------------ high-precision FFT (hp_kernels.cu)

@@ -37,4 +37,64 @@ cudaError_t launch_modswitch(int32_t* out, const int32_t* in, int log2Msize, siz
     return cudaGetLastError();
 }
 
+
+// ---- diagnostics: measured FP64 and read-bandwidth ceilings for the roofline (bench.py)
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double seed) {
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = seed + i + threadIdx.x * 1e-9;
+    const double m = 1.0000000001, c = 1e-12;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = fma(a[i], m, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i];
+    if (s == 12345.678) out[0] = s;     // never true; keeps the chain alive
+}
+cudaError_t probe_fp64(double* tflops) {
+    double* d; cudaError_t e = cudaMalloc(&d, 8); if (e != cudaSuccess) return e;
+    const int grid = 148 * 8, iters = 1 << 16;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    fp64_probe_kernel<<<grid, 256>>>(d, 1024, 1.0);
+    double best = 0;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0);
+        fp64_probe_kernel<<<grid, 256>>>(d, iters, 1.0);
+        cudaEventRecord(e1); e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) break;
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8 * (double)iters * 256 * grid / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
+    return e;
+}
+__global__ void __launch_bounds__(256) read_probe_kernel(const int4* __restrict__ p, size_t n16, int passes, int* sink) {
+    int acc = 0;
+    for (int ps = 0; ps < passes; ps++)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+            int4 v = __ldcg(p + i);
+            acc += v.x ^ v.y ^ v.z ^ v.w;
+        }
+    if (acc == 0x7fffffff) *sink = acc;
+}
+cudaError_t probe_read(size_t bytes, int passes, double* gbs) {
+    void* d; int* sink;
+    cudaError_t e = cudaMalloc(&d, bytes); if (e != cudaSuccess) return e;
+    cudaMalloc(&sink, 4); cudaMemset(d, 1, bytes);
+    const size_t n16 = bytes / 16;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    read_probe_kernel<<<148 * 8, 256>>>((const int4*)d, n16, 1, sink);
+    cudaEventRecord(e0);
+    read_probe_kernel<<<148 * 8, 256>>>((const int4*)d, n16, passes, sink);
+    cudaEventRecord(e1); e = cudaEventSynchronize(e1);
+    float ms = 1; cudaEventElapsedTime(&ms, e0, e1);
+    *gbs = (double)n16 * 16 * passes / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d); cudaFree(sink);
+    return e;
+}
+
 }  // namespace tfhe_b200

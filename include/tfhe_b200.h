@@ -175,6 +175,20 @@ int tfhe_b200_hp_iFFT_batch(tfhe_b200_ctx* ctx, tfhe_b200_cplx96* out_dev, const
 int tfhe_b200_hp_FFT_batch(tfhe_b200_ctx* ctx, int64_t* out_dev, const tfhe_b200_cplx96* in_dev,
                            int N, int count, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Engine diagnostics (no reference counterpart; the reference's only instrumentation is clock() around loops,
+ * cb/poc_CircuitBootstrapping.cpp:1008-1016).  Used by bench.py for the roofline numbers.
+ * ---------------------------------------------------------------------------------------------- */
+/* When enabled, every kernel launch of the batched entry points is bracketed by CUDA events on its stream.
+ * categories: 0 = blind rotation, 1 = key switching, 2 = everything else. */
+int tfhe_b200_profile_enable(tfhe_b200_ctx* ctx, int on);
+/* Synchronises the recorded events, returns summed milliseconds and launch counts per category, then resets. */
+int tfhe_b200_profile_read(tfhe_b200_ctx* ctx, double ms[3], int launches[3]);
+/* Measured FP64 FMA throughput of this GPU (dependent-chain-free DFMA kernel), in TFLOP/s (2 flop per FMA). */
+int tfhe_b200_probe_fp64_tflops(tfhe_b200_ctx* ctx, double* tflops);
+/* Measured read bandwidth over a `bytes`-sized buffer that is re-read `passes` times (L2-resident when small), GB/s. */
+int tfhe_b200_probe_read_gbs(tfhe_b200_ctx* ctx, size_t bytes, int passes, double* gbs);
+
 #ifdef __cplusplus
 }
 #endif

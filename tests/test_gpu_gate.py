@@ -21,8 +21,9 @@ def dev(a):
 
 
 def test_fft_roundtrip_and_product(engine):
-    """fft(ifft(x)) == x exactly for small ints; FFT product within 1 LSB of the exact negacyclic product
-    (reference bar: asm==model 1e-5, round trip == (N/2) x, cb/spqlios/spqlios-bench.cpp:63-77)."""
+    """fft(ifft(x)) == x within 1 LSB (the reference truncates toward zero, fft_processor_spqlios.cpp:102, and is itself
+    only 1-LSB exact: tests/golden/fft_roundtrip_spqlios_N1024.i32); FFT product within 1 LSB of the exact negacyclic
+    product (reference bar: asm==model 1e-5, round trip == (N/2) x, cb/spqlios/spqlios-bench.cpp:63-77)."""
     rng = np.random.default_rng(7)
     for N in (1024, 2048):
         B = 8
@@ -33,7 +34,7 @@ def test_fft_roundtrip_and_product(engine):
         engine.IntPolynomial_ifft(spec, dx, N, B)
         engine.TorusPolynomial_fft(back, spec, N, B)
         torch.cuda.synchronize()
-        assert np.array_equal(back.cpu().numpy(), x)
+        assert np.abs(back.cpu().numpy() - x).max() <= 1
         # product: 4 digit polynomials (|d| <= 512) times 4 torus polynomials, accumulated (the lvl-1 CMUX shape)
         t = rng.integers(-2**31, 2**31 - 1, size=(B, N), dtype=np.int64).astype(np.int32)
         st = torch.empty((B, N), dtype=torch.float64, device=DEV)
