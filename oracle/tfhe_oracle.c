@@ -548,6 +548,14 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+void orc_tfhe_bootstrap_woKS_FFT_batch(Torus32* result, const orc_gate_keys* K, Torus32 mu, const Torus32* x, int count, int threads) {
+    const size_t si = (size_t)K->p.n + 1, so = (size_t)K->p.N + 1;
+    (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 0 ? threads : omp_get_max_threads())
+#endif
+    for (int g = 0; g < count; g++) orc_tfhe_bootstrap_woKS_FFT(result + g * so, K, mu, x + g * si);
+}
 void orc_bootsGate_batch(Torus32* result, int op, const Torus32* ca, const Torus32* cb, const orc_gate_keys* K, int count, int threads) {
     const size_t s = (size_t)K->p.n + 1;
     (void)threads;

@@ -135,6 +135,7 @@ void orc_bootsSymEncrypt(Torus32* result, int message, const orc_gate_keys* K, o
 int  orc_bootsSymDecrypt(const Torus32* sample, const orc_gate_keys* K);
 int  orc_gate_plain(int op, int a, int b);
 /* OpenMP batch (the reference's only threading idiom, par/test_parallel_multiplications.cpp:62) */
+void orc_tfhe_bootstrap_woKS_FFT_batch(Torus32* result, const orc_gate_keys* K, Torus32 mu, const Torus32* x, int count, int threads);
 void orc_bootsGate_batch(Torus32* result, int op, const Torus32* ca, const Torus32* cb, const orc_gate_keys* K, int count, int threads);
 int  orc_num_threads(void);
 

@@ -163,8 +163,7 @@ class GateOracle:
     def bootstrap_woKS(self, mu, x):
         x = np.ascontiguousarray(x, np.int32)
         out = np.empty((len(x), self.N + 1), np.int32)
-        for i in range(len(x)):
-            lib().orc_tfhe_bootstrap_woKS_FFT(p(out[i]), self.K, mu, p(x[i]))
+        lib().orc_tfhe_bootstrap_woKS_FFT_batch(p(out), self.K, ctypes.c_int32(mu), p(x), len(x), 0)
         return out
 
     def bootstrap(self, mu, x):
