@@ -1,8 +1,8 @@
 // br_kernels.cu -- fused blind rotation for sm_100a.
 //
-// One thread GROUP (T = N/16 threads: 64 for N=1024, 128 for N=2048) owns one TLWE accumulator for all n
-// CMUX steps; the accumulator lives in shared memory for the whole kernel and is touched in HBM only
-// at the start (input LWE sample) and at the end (extracted LWE sample).  Per step the group fuses
+// One lane GROUP (T = N/32 lanes: one warp for N=1024, two warps for N=2048) owns one TLWE accumulator for all n
+// CMUX steps; the accumulator lives in shared memory for the whole kernel and is touched in HBM only at the start
+// (input LWE sample) and at the end (extracted LWE sample).  Per step the group fuses
 //   (X^a - 1) * ACC            tLweMulByXaiMinusOne         cb/tlwe_functions.cpp:209-213
 //   gadget decomposition       tGswTorus32PolynomialDecompH cb/tgsw_functions.cpp:224-337
 //                              tGswTorus64PolynomialDecompH cb/poc_CircuitBootstrapping.cpp:492-515
@@ -10,13 +10,17 @@
 //   2l x 2 spectral MACs       tLweFFTAddMulRTo             cb/tlwe_functions.cpp:318-325
 //   2 backward transforms      tLweFromFFTConvert           cb/tlwe_functions.cpp:299-305
 //   ACC += result              tLweAddTo                    cb/tlwe_functions.cpp:163-170
-// i.e. tfhe_MuxRotate_FFT (cb/lwe_functions.cpp:328-333) inside the loop of tfhe_blindRotate_FFT
-// (:337-361), plus modulus switch, test-vector rotation and sample extraction on either side
-// (tfhe_bootstrap_woKS_FFT :399-430; circuitBootstrapWoKS cb/poc_CircuitBootstrapping.cpp:530-659).
+// i.e. tfhe_MuxRotate_FFT (cb/lwe_functions.cpp:328-333) inside the loop of tfhe_blindRotate_FFT (:337-361), plus
+// modulus switch, test-vector rotation and sample extraction on either side (tfhe_bootstrap_woKS_FFT :399-430;
+// circuitBootstrapWoKS cb/poc_CircuitBootstrapping.cpp:530-659).
 //
+// The spectra of the 2l digit polynomials never leave registers: each lane multiply-accumulates its 16 spectrum
+// slots against the bootstrapping-key spectra (read with coalesced 16-byte loads, L2 resident) into two register
+// accumulators, which the two backward transforms then consume.  N=1024 groups are single warps, so the only
+// synchronisation inside a CMUX is __syncwarp around the transpose.
 // The reference's `if (barai==0) continue` (:350) is kept (group-uniform branch).
 #include "engine.h"
-#include "fft_device.cuh"
+#include "tree_fft.cuh"
 
 namespace tfhe_b200 {
 
@@ -46,80 +50,109 @@ __device__ __forceinline__ int modswitch32(int32_t x, int log2Msize) {
     return (int)(phase64 >> (64 - log2Msize));
 }
 
+template <int LOGM>
+__device__ __forceinline__ void mac_bk(cplx (&R0)[16], cplx (&R1)[16], const cplx (&v)[16], const cplx* __restrict__ bkp) {
+    constexpr int T = TreePlan<LOGM>::T, M = TreePlan<LOGM>::M;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const cplx b0 = __ldg(bkp + i * T);
+        const cplx b1 = __ldg(bkp + M + i * T);
+        cfma(R0[i], v[i], b0);
+        cfma(R1[i], v[i], b1);
+    }
+}
+
 // One CMUX: ACC <- ACC + BK_i (x) ((X^a - 1) ACC).   acc: shared [2][N].  bk: [2l][2][M] spectra (scaled 2/N).
-template <int LOGM, typename Torus>
+// LT == 2: both gadget digits of a coefficient come from one accumulator read (the second is parked, packed, in a
+// lane-private shared-memory word); otherwise the accumulator is re-read per level.
+template <int LOGM, typename Torus, int LT>
 __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, const cplx* __restrict__ bk,
-                                          const int l, const int Bgbit, cplx* __restrict__ buf,
+                                          const int l, const int Bgbit, cplx* __restrict__ buf, uint32_t* __restrict__ pk,
                                           const cplx* __restrict__ tw, const int t, const int bar_id) {
-    typedef FftPlan<LOGM> P;
+    typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
     constexpr int M = P::M, N = P::N, T = P::T, W = TorusTraits<Torus>::W;
     const U offset = decomp_offset((U)0, l, Bgbit);
     const uint32_t mask = (1u << Bgbit) - 1u;
     const int half = 1 << (Bgbit - 1);
 
-    cplx R0[8], R1[8];
+    cplx R0[16], R1[16];
 #pragma unroll
-    for (int e = 0; e < 8; e++) { R0[e] = make_double2(0.0, 0.0); R1[e] = make_double2(0.0, 0.0); }
+    for (int e = 0; e < 16; e++) { R0[e] = make_double2(0.0, 0.0); R1[e] = make_double2(0.0, 0.0); }
 
 #pragma unroll 1
     for (int q = 0; q < 2; q++) {
-        U ure[8], uim[8];
+        const Torus* __restrict__ aq = acc + q * N;
+        if (LT == 2) {
+            cplx v[16];
+            const int sh0 = W - Bgbit, sh1 = W - 2 * Bgbit;
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int j = t + T * r;
-            ure[r] = (U)rot_minus_one<Torus, N>(acc + q * N, j, a) + offset;
-            uim[r] = (U)rot_minus_one<Torus, N>(acc + q * N, j + M, a) + offset;
-        }
+            for (int m = 0; m < 16; m++) {
+                const int j = t + T * m;
+                const U ure = (U)rot_minus_one<Torus, N>(aq, j, a) + offset;
+                const U uim = (U)rot_minus_one<Torus, N>(aq, j + M, a) + offset;
+                v[m] = make_double2((double)((int)((uint32_t)(ure >> sh0) & mask) - half),
+                                    (double)((int)((uint32_t)(uim >> sh0) & mask) - half));
+                const uint32_t d1r = (uint32_t)((int)((uint32_t)(ure >> sh1) & mask) - half);
+                const uint32_t d1i = (uint32_t)((int)((uint32_t)(uim >> sh1) & mask) - half);
+                pk[m * T + t] = (d1r & 0xFFFFu) | (d1i << 16);     // lane-private slot, parked in shared memory
+            }
+            tree_forward<LOGM>(v, buf, tw, t, bar_id);
+            mac_bk<LOGM>(R0, R1, v, bk + (size_t)((q * 2 + 0) * 2) * M + t);
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                const uint32_t w1 = pk[m * T + t];
+                v[m] = make_double2((double)((int)(w1 << 16) >> 16), (double)((int)w1 >> 16));
+            }
+            tree_forward<LOGM>(v, buf, tw, t, bar_id);
+            mac_bk<LOGM>(R0, R1, v, bk + (size_t)((q * 2 + 1) * 2) * M + t);
+        } else {
 #pragma unroll 1
-        for (int lev = 0; lev < l; lev++) {
-            const int sh = W - (lev + 1) * Bgbit;
-            cplx v[8];
+            for (int lev = 0; lev < l; lev++) {
+                const int sh = W - (lev + 1) * Bgbit;
+                cplx v[16];
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const double dre = (double)((int)((uint32_t)(ure[r] >> sh) & mask) - half);
-                const double dim = (double)((int)((uint32_t)(uim[r] >> sh) & mask) - half);
-                v[r] = cmul(make_double2(dre, dim), tw[P::TW_TWIST + t + T * r]);
-            }
-            fft_forward<LOGM>(v, buf, tw, t, bar_id);
-            const cplx* __restrict__ bk0 = bk + (size_t)((q * l + lev) * 2) * M + t;
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const cplx b0 = __ldg(bk0 + e * T);
-                const cplx b1 = __ldg(bk0 + M + e * T);
-                cfma(R0[e], v[e], b0);
-                cfma(R1[e], v[e], b1);
+                for (int m = 0; m < 16; m++) {
+                    const int j = t + T * m;
+                    const U ure = (U)rot_minus_one<Torus, N>(aq, j, a) + offset;
+                    const U uim = (U)rot_minus_one<Torus, N>(aq, j + M, a) + offset;
+                    v[m] = make_double2((double)((int)((uint32_t)(ure >> sh) & mask) - half),
+                                        (double)((int)((uint32_t)(uim >> sh) & mask) - half));
+                }
+                tree_forward<LOGM>(v, buf, tw, t, bar_id);
+                mac_bk<LOGM>(R0, R1, v, bk + (size_t)((q * l + lev) * 2) * M + t);
             }
         }
     }
-    fft_backward<LOGM>(R0, buf, tw, t, bar_id);
+    // every lane has finished reading the accumulator once it passes the first sync inside tree_backward
+    tree_backward<LOGM>(R0, buf, tw, t, bar_id);
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const int j = t + T * r;
-        acc[j] = (Torus)((U)acc[j] + (U)to_torus(R0[r].x, (Torus)0));
-        acc[j + M] = (Torus)((U)acc[j + M] + (U)to_torus(R0[r].y, (Torus)0));
+    for (int m = 0; m < 16; m++) {
+        const int j = t + T * m;
+        acc[j] = (Torus)((U)acc[j] + (U)to_torus(R0[m].x, (Torus)0));
+        acc[j + M] = (Torus)((U)acc[j + M] + (U)to_torus(R0[m].y, (Torus)0));
     }
-    fft_backward<LOGM>(R1, buf, tw, t, bar_id);
+    tree_backward<LOGM>(R1, buf, tw, t, bar_id);
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const int j = t + T * r;
-        acc[N + j] = (Torus)((U)acc[N + j] + (U)to_torus(R1[r].x, (Torus)0));
-        acc[N + j + M] = (Torus)((U)acc[N + j + M] + (U)to_torus(R1[r].y, (Torus)0));
+    for (int m = 0; m < 16; m++) {
+        const int j = t + T * m;
+        acc[N + j] = (Torus)((U)acc[N + j] + (U)to_torus(R1[m].x, (Torus)0));
+        acc[N + j + M] = (Torus)((U)acc[N + j + M] + (U)to_torus(R1[m].y, (Torus)0));
     }
-    group_sync(bar_id, T);      // accumulator writes visible before the next step's rotated reads
+    lanes_sync<T>(bar_id);      // accumulator writes visible before the next step's rotated reads
 }
 
 template <int LOGM, typename Torus, int GROUPS> struct BRSmem {
-    typedef FftPlan<LOGM> P;
-    static constexpr int NPAD = 1024;   // room for bara (n <= 1024)
+    typedef TreePlan<LOGM> P;
+    static constexpr int NPAD = 1024;   // room for bara (n <= 1023, plus b)
     static constexpr size_t TW_BYTES = sizeof(cplx) * ((P::TW_TOTAL + 1) & ~1);
-    static constexpr size_t GROUP_BYTES = sizeof(cplx) * P::BUF + sizeof(Torus) * 2 * P::N + sizeof(int32_t) * NPAD;
+    static constexpr size_t GROUP_BYTES = sizeof(cplx) * P::BUF + sizeof(Torus) * 2 * P::N + sizeof(int32_t) * NPAD + sizeof(uint32_t) * 16 * P::T;
     static constexpr size_t TOTAL = TW_BYTES + GROUPS * GROUP_BYTES;
 };
 
-template <int LOGM, typename Torus, int GROUPS, int MINB>
-__global__ void __launch_bounds__(GROUPS * FftPlan<LOGM>::T, MINB) blind_rotate_kernel(const BRArgs A) {
-    typedef FftPlan<LOGM> P;
+template <int LOGM, typename Torus, int GROUPS, int LT>
+__global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_kernel(const BRArgs A) {
+    typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
     typedef BRSmem<LOGM, Torus, GROUPS> S;
     constexpr int M = P::M, N = P::N, T = P::T;
@@ -134,11 +167,12 @@ __global__ void __launch_bounds__(GROUPS * FftPlan<LOGM>::T, MINB) blind_rotate_
     cplx* buf = reinterpret_cast<cplx*>(gbase);
     Torus* acc = reinterpret_cast<Torus*>(gbase + sizeof(cplx) * P::BUF);
     int32_t* bara = reinterpret_cast<int32_t*>(gbase + sizeof(cplx) * P::BUF + sizeof(Torus) * 2 * N);
+    uint32_t* pk = reinterpret_cast<uint32_t*>(bara + S::NPAD);
 
     // unit = (sample, test-vector index); n_mu > 1 only on the circuit-bootstrap path
     const int n_mu = A.n_mu > 0 ? A.n_mu : 1;
     const long unit = (long)blockIdx.x * GROUPS + g;
-    if (unit >= (long)A.count * n_mu) return;          // whole group leaves; named barriers are per group
+    if (unit >= (long)A.count * n_mu) return;          // whole group leaves; its barriers are private to it
     const int ct = (int)(unit / n_mu), w = (int)(unit % n_mu);
     const int n = A.n;
 
@@ -162,13 +196,13 @@ __global__ void __launch_bounds__(GROUPS * FftPlan<LOGM>::T, MINB) blind_rotate_
             for (int i = t; i <= n; i += T) bara[i] = ab[i];
             if (A.mu_bgbit > 0) mu = (Torus)(1ull << (64 - (w + 1) * A.mu_bgbit));   // mu_w, poc:846
         }
-        group_sync(bar_id, T);
+        lanes_sync<T>(bar_id);
         barb = bara[n];
     } else {
         const int32_t* ab = A.bara + (size_t)ct * n;
         for (int i = t; i < n; i += T) bara[i] = ab[i];
         if (A.mode == BR_TESTVEC) barb = A.barb[ct];
-        group_sync(bar_id, T);
+        lanes_sync<T>(bar_id);
     }
 
     if (A.mode == BR_ACCUM) {
@@ -189,14 +223,14 @@ __global__ void __launch_bounds__(GROUPS * FftPlan<LOGM>::T, MINB) blind_rotate_
             acc[N + j] = (idx & N) ? (Torus)(0 - (U)val) : val;
         }
     }
-    group_sync(bar_id, T);
+    lanes_sync<T>(bar_id);
 
     // ---- n CMUX steps (tfhe_blindRotate_FFT :348-354)
     const size_t bk_stride = (size_t)2 * A.l * 2 * M;
     for (int i = 0; i < n; i++) {
         const int a = bara[i];
         if (a == 0) continue;
-        cmux_step<LOGM, Torus>(acc, a, A.bkfft + (size_t)i * bk_stride, A.l, A.Bgbit, buf, tw, t, bar_id);
+        cmux_step<LOGM, Torus, LT>(acc, a, A.bkfft + (size_t)i * bk_stride, LT == 2 ? 2 : A.l, A.Bgbit, buf, pk, tw, t, bar_id);
     }
 
     // ---- epilogue
@@ -216,16 +250,17 @@ __global__ void __launch_bounds__(GROUPS * FftPlan<LOGM>::T, MINB) blind_rotate_
 }
 
 static bool g_inited = false;
-constexpr int G32 = 4, G64 = 2;
+constexpr int G32 = 8, G64 = 3;     // accumulators per CTA: 8 warps (N=1024) / 3 x 2 warps (N=2048)
 
+template <int LOGM, typename Torus, int GROUPS, int LT> static cudaError_t br_attr() {
+    return cudaFuncSetAttribute(blind_rotate_kernel<LOGM, Torus, GROUPS, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)BRSmem<LOGM, Torus, GROUPS>::TOTAL);
+}
 cudaError_t blind_rotate_init() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(blind_rotate_kernel<9, int32_t, G32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)BRSmem<9, int32_t, G32>::TOTAL);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(blind_rotate_kernel<10, int64_t, G64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)BRSmem<10, int64_t, G64>::TOTAL);
-    if (e != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, G32, 2>()) != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, G32, 0>()) != cudaSuccess) return e;
+    if ((e = br_attr<10, int64_t, G64, 0>()) != cudaSuccess) return e;
     g_inited = true;
     return cudaSuccess;
 }
@@ -234,7 +269,9 @@ cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
     if (!g_inited) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
     if (a.count <= 0) return cudaSuccess;
     const int grid = (a.count + G32 - 1) / G32;
-    blind_rotate_kernel<9, int32_t, G32, 1><<<grid, G32 * FftPlan<9>::T, BRSmem<9, int32_t, G32>::TOTAL, s>>>(a);
+    const size_t smem = BRSmem<9, int32_t, G32>::TOTAL;
+    if (a.l == 2) blind_rotate_kernel<9, int32_t, G32, 2><<<grid, G32 * TreePlan<9>::T, smem, s>>>(a);
+    else          blind_rotate_kernel<9, int32_t, G32, 0><<<grid, G32 * TreePlan<9>::T, smem, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
@@ -242,85 +279,91 @@ cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
     if (a.count <= 0) return cudaSuccess;
     const long units = (long)a.count * (a.n_mu > 0 ? a.n_mu : 1);
     const int grid = (int)((units + G64 - 1) / G64);
-    blind_rotate_kernel<10, int64_t, G64, 1><<<grid, G64 * FftPlan<10>::T, BRSmem<10, int64_t, G64>::TOTAL, s>>>(a);
+    blind_rotate_kernel<10, int64_t, G64, 0><<<grid, G64 * TreePlan<10>::T, BRSmem<10, int64_t, G64>::TOTAL, s>>>(a);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
-// Standalone transforms (one group of T threads per polynomial, 4 polynomials per CTA)
+// Standalone transforms (one lane group per polynomial, 256 threads per CTA)
 // ---------------------------------------------------------------------------------------------
+template <int LOGM> struct TrCfg {
+    typedef TreePlan<LOGM> P;
+    static constexpr int GROUPS = 256 / P::T;
+    static constexpr size_t SMEM = sizeof(cplx) * (((P::TW_TOTAL + 1) & ~1) + GROUPS * P::BUF);
+};
+
 template <int LOGM, typename Torus>
-__global__ void __launch_bounds__(4 * FftPlan<LOGM>::T) poly_to_spectrum_kernel(cplx* __restrict__ out, const Torus* __restrict__ in,
-                                                                                const cplx* __restrict__ twg, int count, double scale) {
-    typedef FftPlan<LOGM> P;
+__global__ void __launch_bounds__(256) poly_to_spectrum_kernel(cplx* __restrict__ out, const Torus* __restrict__ in,
+                                                               const cplx* __restrict__ twg, int count, double scale) {
+    typedef TreePlan<LOGM> P;
     constexpr int M = P::M, N = P::N, T = P::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* tw = reinterpret_cast<cplx*>(smem_raw);
-    for (int i = threadIdx.x; i < P::TW_TOTAL; i += 4 * T) tw[i] = twg[i];
+    for (int i = threadIdx.x; i < P::TW_TOTAL; i += 256) tw[i] = twg[i];
     __syncthreads();
     const int g = threadIdx.x / T, t = threadIdx.x % T;
     cplx* buf = tw + ((P::TW_TOTAL + 1) & ~1) + g * P::BUF;
-    const long poly = (long)blockIdx.x * 4 + g;
+    const long poly = (long)blockIdx.x * TrCfg<LOGM>::GROUPS + g;
     if (poly >= count) return;
     const Torus* src = in + (size_t)poly * N;
-    cplx v[8];
+    cplx v[16];
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const int j = t + T * r;
+    for (int m = 0; m < 16; m++) {
+        const int j = t + T * m;
         // execute_reverse_int: exact int->double (:33-46); execute_reverse_torus64: C cast, round to 53 bits (:166-170)
-        v[r] = cmul(make_double2((double)src[j], (double)src[j + M]), tw[P::TW_TWIST + j]);
+        v[m] = make_double2((double)src[j], (double)src[j + M]);
     }
-    fft_forward<LOGM>(v, buf, tw, t, 1 + g);
+    tree_forward<LOGM>(v, buf, tw, t, 1 + g);
     cplx* dst = out + (size_t)poly * M + t;
 #pragma unroll
-    for (int e = 0; e < 8; e++) dst[e * T] = make_double2(v[e].x * scale, v[e].y * scale);
+    for (int i = 0; i < 16; i++) dst[i * T] = make_double2(v[i].x * scale, v[i].y * scale);
 }
 
 template <int LOGM, typename Torus>
-__global__ void __launch_bounds__(4 * FftPlan<LOGM>::T) spectrum_to_torus_kernel(Torus* __restrict__ out, const cplx* __restrict__ in,
-                                                                                 const cplx* __restrict__ twg, int count, double scale) {
-    typedef FftPlan<LOGM> P;
+__global__ void __launch_bounds__(256) spectrum_to_torus_kernel(Torus* __restrict__ out, const cplx* __restrict__ in,
+                                                                const cplx* __restrict__ twg, int count, double scale) {
+    typedef TreePlan<LOGM> P;
     constexpr int M = P::M, N = P::N, T = P::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* tw = reinterpret_cast<cplx*>(smem_raw);
-    for (int i = threadIdx.x; i < P::TW_TOTAL; i += 4 * T) tw[i] = twg[i];
+    for (int i = threadIdx.x; i < P::TW_TOTAL; i += 256) tw[i] = twg[i];
     __syncthreads();
     const int g = threadIdx.x / T, t = threadIdx.x % T;
     cplx* buf = tw + ((P::TW_TOTAL + 1) & ~1) + g * P::BUF;
-    const long poly = (long)blockIdx.x * 4 + g;
+    const long poly = (long)blockIdx.x * TrCfg<LOGM>::GROUPS + g;
     if (poly >= count) return;
     const cplx* src = in + (size_t)poly * M + t;
-    cplx v[8];
+    cplx v[16];
 #pragma unroll
-    for (int e = 0; e < 8; e++) { cplx x = src[e * T]; v[e] = make_double2(x.x * scale, x.y * scale); }   // 2/N pre-scale (:78-100)
-    fft_backward<LOGM>(v, buf, tw, t, 1 + g);
+    for (int i = 0; i < 16; i++) { cplx x = src[i * T]; v[i] = make_double2(x.x * scale, x.y * scale); }   // 2/N pre-scale (:78-100)
+    tree_backward<LOGM>(v, buf, tw, t, 1 + g);
     Torus* dst = out + (size_t)poly * N;
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const int j = t + T * r;
-        dst[j] = to_torus(v[r].x, (Torus)0);
-        dst[j + M] = to_torus(v[r].y, (Torus)0);
+    for (int m = 0; m < 16; m++) {
+        const int j = t + T * m;
+        dst[j] = to_torus(v[m].x, (Torus)0);
+        dst[j + M] = to_torus(v[m].y, (Torus)0);
     }
 }
-
-template <int LOGM> static size_t tr_smem() { return sizeof(cplx) * (((FftPlan<LOGM>::TW_TOTAL + 1) & ~1) + 4 * FftPlan<LOGM>::BUF); }
 
 template <int LOGM, typename Torus>
 static cudaError_t launch_p2s(cplx* out, const Torus* in, const cplx* tw, int count, double scale, cudaStream_t s) {
     auto kern = poly_to_spectrum_kernel<LOGM, Torus>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem<LOGM>());
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TrCfg<LOGM>::SMEM);
     if (e != cudaSuccess) return e;
     if (count <= 0) return cudaSuccess;
-    kern<<<(count + 3) / 4, 4 * FftPlan<LOGM>::T, tr_smem<LOGM>(), s>>>(out, in, tw, count, scale);
+    const int G = TrCfg<LOGM>::GROUPS;
+    kern<<<(count + G - 1) / G, 256, TrCfg<LOGM>::SMEM, s>>>(out, in, tw, count, scale);
     return cudaGetLastError();
 }
 template <int LOGM, typename Torus>
 static cudaError_t launch_s2t(Torus* out, const cplx* in, const cplx* tw, int count, double scale, cudaStream_t s) {
     auto kern = spectrum_to_torus_kernel<LOGM, Torus>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr_smem<LOGM>());
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TrCfg<LOGM>::SMEM);
     if (e != cudaSuccess) return e;
     if (count <= 0) return cudaSuccess;
-    kern<<<(count + 3) / 4, 4 * FftPlan<LOGM>::T, tr_smem<LOGM>(), s>>>(out, in, tw, count, scale);
+    const int G = TrCfg<LOGM>::GROUPS;
+    kern<<<(count + G - 1) / G, 256, TrCfg<LOGM>::SMEM, s>>>(out, in, tw, count, scale);
     return cudaGetLastError();
 }
 

@@ -9,7 +9,7 @@ namespace tfhe_b200 {
 
 typedef double2 cplx;
 
-// host-side twiddle generation (twiddles.cpp): FftPlan<LOGM> layout, entries are (re,im) pairs
+// host-side twiddle generation (twiddles.cpp): TreePlan<LOGM> layout (tree_fft.cuh), entries are (re,im) pairs
 void make_fft_tables(int logM, double* out /* 2 * TW_TOTAL doubles */);
 int  fft_table_entries(int logM);
 // hp tables: 2N entries of {re_lo,re_hi,im_lo,im_hi}; inverse=0 -> powomega, 1 -> powombar (hp/code.cpp:378-388)
@@ -19,7 +19,7 @@ void make_hp_tables(int n2N, int inverse, uint64_t* out /* 4 * n2N words */);
 enum BRMode { BR_ACCUM = 0, BR_TESTVEC = 1, BR_LWE = 2 };
 struct BRArgs {
     const cplx* bkfft;    // [n][2l][2][M] spectra, pre-scaled by 2/N
-    const cplx* tw;       // FftPlan table
+    const cplx* tw;       // TreePlan table
     int n, l, Bgbit, count, mode;
     // BR_ACCUM  : accum[B][2][N] in/out, bara[B][n]
     // BR_TESTVEC: v[N], barb[B], bara[B][n] -> out[B][N+1]

@@ -1,0 +1,237 @@
+// tree_fft.cuh -- warp-resident negacyclic FP64 transform for sm_100a ("twist-free" product-tree form).
+//
+// Replaces the reference's AVX2 kernels cb/spqlios/spqlios-ifft-fma.s:63-263 (coefficients -> spectrum) and
+// cb/spqlios/spqlios-fft-fma.s:79-274 (spectrum -> coefficients) and their wrappers
+// (cb/spqlios/fft_processor_spqlios.cpp:27-170).  Same mathematics as SURVEY A.7 -- fold the N real coefficients
+// into M = N/2 complex z_j = c_j + i c_{j+M}; multiplication mod X^N+1 becomes multiplication mod X^M - i --
+// but a different algorithm, chosen for the B200's FP64 : shared-memory ratio (64 FMA vs 128 B per clock per SM):
+//
+//   * Instead of "twist by w^j, then cyclic FFT", the transform walks the product tree of X^M - i:
+//       X^L - c = (X^(L/2) - sqrt c)(X^(L/2) + sqrt c),  butterfly (lo, hi) -> (lo + w hi, lo - w hi), w = sqrt c.
+//     Every twiddle belongs to a tree NODE, not to a coefficient, so the first four levels use warp-uniform constants
+//     and there is no separate twist pass; a forward butterfly is 6 FMAs.
+//   * T = M/16 lanes own one polynomial (one warp for N=1024, two for N=2048), 16 points per lane in registers:
+//     depths 0-3 in registers, ONE transpose through shared memory, depths 4-7 in registers, and the last
+//     log2(M)-8 depths by a half-register exchange with the neighbouring lane (__shfl_xor).
+//     For N=1024 that is 128 B/lane of shared-memory traffic each way plus 32 shuffles per transform.
+//   * Sibling nodes have twiddles (w, i w): only every other twiddle is stored/loaded.
+//
+// The spectral order is engine-private (leaf order of the tree, distributed over lanes); bk spectra are produced by
+// this same code, so products line up slot by slot.   tools/tree_fft_model.py is the lane-level numpy model.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tfhe_b200 {
+
+typedef double2 cplx;
+
+__device__ __forceinline__ cplx cmulf(cplx a, cplx b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+// acc += a*b
+__device__ __forceinline__ void cfma(cplx& acc, cplx a, cplx b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+
+// forward butterfly at a node with twiddle w:  lo' = lo + w hi ; hi' = lo - w hi      (6 FMA)
+__device__ __forceinline__ void bf_fwd(cplx& lo, cplx& hi, const cplx w) {
+    double xr = fma(w.x, hi.x, lo.x); xr = fma(-w.y, hi.y, xr);
+    double xi = fma(w.x, hi.y, lo.y); xi = fma(w.y, hi.x, xi);
+    hi.x = fma(2.0, lo.x, -xr); hi.y = fma(2.0, lo.y, -xi);
+    lo.x = xr; lo.y = xi;
+}
+// same with twiddle i*w (the sibling node)
+__device__ __forceinline__ void bf_fwd_i(cplx& lo, cplx& hi, const cplx w) {
+    double xr = fma(-w.x, hi.y, lo.x); xr = fma(-w.y, hi.x, xr);
+    double xi = fma(w.x, hi.x, lo.y); xi = fma(-w.y, hi.y, xi);
+    hi.x = fma(2.0, lo.x, -xr); hi.y = fma(2.0, lo.y, -xi);
+    lo.x = xr; lo.y = xi;
+}
+// inverse butterfly:  lo' = lo + hi ; hi' = (lo - hi) conj(w)      (unscaled: the 1/M is folded into the key spectra)
+__device__ __forceinline__ void bf_inv(cplx& lo, cplx& hi, const cplx w) {
+    const double dr = lo.x - hi.x, di = lo.y - hi.y;
+    lo.x += hi.x; lo.y += hi.y;
+    hi.x = fma(dr, w.x, di * w.y);
+    hi.y = fma(di, w.x, -dr * w.y);
+}
+// inverse with twiddle i*w: conj(i w) = -i conj(w)
+__device__ __forceinline__ void bf_inv_i(cplx& lo, cplx& hi, const cplx w) {
+    const double dr = lo.x - hi.x, di = lo.y - hi.y;
+    lo.x += hi.x; lo.y += hi.y;
+    hi.x = fma(di, w.x, -dr * w.y);
+    hi.y = fma(-dr, w.x, -di * w.y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Geometry and twiddle-table layout (cplx entries), LOGM = log2(M) in {9, 10}
+//   TA  [8]        depths 0-3, essential (even) nodes: (0,0) (1,0) (2,0) (2,2) (3,0) (3,2) (3,4) (3,6)
+//   TB  [8][16]    depths 4-7 under depth-4 node b: (4,b) (5,2b) (6,4b) (6,4b+2) (7,8b+2k), k<4     index e*16+b
+//   TC0 [4][M/16]  depth 8, lane group g: nodes 8g+2k, k<4                                         index k*(M/16)+g
+//   TC1 [8][T]     depth 9 (M=1024 only), lane t: nodes 16(t>>1)+2k+(t&1), k<8                     index k*T+t
+//   node twiddle w(d,nu) = exp(2 pi i (1 + 4 bitrev_d(nu)) / 2^(d+3))
+// ---------------------------------------------------------------------------------------------
+template <int LOGM> struct TreePlan {
+    static constexpr int M = 1 << LOGM;
+    static constexpr int N = 2 * M;
+    static constexpr int T = M / 16;               // lanes per polynomial
+    static constexpr int P = T / 16;               // lanes per depth-4 node
+    static constexpr int NS = LOGM - 8;            // shuffle stages
+    static constexpr int S = T + T / 16;           // padded row stride of the transpose buffer
+    static constexpr int BUF = 16 * S;             // cplx entries per polynomial
+    static constexpr int G0 = T >> (NS - 1);       // lane groups at depth 8 (= 32 for both sizes)
+    static constexpr int TA = 0;
+    static constexpr int TB = 8;
+    static constexpr int TC0 = TB + 128;
+    static constexpr int TC1 = TC0 + 4 * G0;
+    static constexpr int TW_TOTAL = TC1 + (NS > 1 ? 8 * T : 0);
+};
+
+template <int T> __device__ __forceinline__ void lanes_sync(int bar_id) {
+    if (T == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
+}
+
+// four tree depths on the 16 registers of a lane; E = the 8 essential twiddles of these depths
+template <bool INV> __device__ __forceinline__ void pass16(cplx (&v)[16], const cplx* __restrict__ E, const int estride) {
+    if (!INV) {
+        {   const cplx w = E[0];
+#pragma unroll
+            for (int i = 0; i < 8; i++) bf_fwd(v[i], v[i + 8], w); }
+        {   const cplx w = E[estride];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { bf_fwd(v[i], v[i + 4], w); bf_fwd_i(v[8 + i], v[12 + i], w); } }
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const cplx w = E[(2 + s) * estride];
+#pragma unroll
+            for (int i = 0; i < 2; i++) { bf_fwd(v[8 * s + i], v[8 * s + i + 2], w); bf_fwd_i(v[8 * s + 4 + i], v[8 * s + 6 + i], w); }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const cplx w = E[(4 + s) * estride];
+            bf_fwd(v[4 * s], v[4 * s + 1], w); bf_fwd_i(v[4 * s + 2], v[4 * s + 3], w);
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const cplx w = E[(4 + s) * estride];
+            bf_inv(v[4 * s], v[4 * s + 1], w); bf_inv_i(v[4 * s + 2], v[4 * s + 3], w);
+        }
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const cplx w = E[(2 + s) * estride];
+#pragma unroll
+            for (int i = 0; i < 2; i++) { bf_inv(v[8 * s + i], v[8 * s + i + 2], w); bf_inv_i(v[8 * s + 4 + i], v[8 * s + 6 + i], w); }
+        }
+        {   const cplx w = E[estride];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { bf_inv(v[i], v[i + 4], w); bf_inv_i(v[8 + i], v[12 + i], w); } }
+        {   const cplx w = E[0];
+#pragma unroll
+            for (int i = 0; i < 8; i++) bf_inv(v[i], v[i + 8], w); }
+    }
+}
+
+// lane(h=0).v[8+k] <-> lane(h=1).v[k] with the lane at distance `mask`: afterwards every lane owns complete (lo,hi)
+// pairs (v[k], v[8+k]).  An involution: the inverse transform applies it again.
+__device__ __forceinline__ void half_swap(cplx (&v)[16], const int mask, const bool h) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const cplx a = v[k], c = v[8 + k];
+        cplx x = h ? a : c;
+        x.x = __shfl_xor_sync(0xffffffffu, x.x, mask);
+        x.y = __shfl_xor_sync(0xffffffffu, x.y, mask);
+        v[k] = h ? x : a;
+        v[8 + k] = h ? c : x;
+    }
+}
+
+// Forward: in  v[m] = z_{t + T m}  (t = lane in [0,T), natural coefficient order, stride T)
+//          out v[i] = spectrum slot i of this lane (leaf order, private)
+template <int LOGM>
+__device__ __forceinline__ void tree_forward(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id) {
+    typedef TreePlan<LOGM> P;
+    constexpr int T = P::T;
+    pass16<false>(v, tw + P::TA, 1);
+    lanes_sync<T>(bar_id);                                   // WAR: previous transform's reads of buf
+#pragma unroll
+    for (int m = 0; m < 16; m++) buf[m * P::S + t] = v[m];
+    lanes_sync<T>(bar_id);
+    const int b = t / P::P, p = t % P::P;
+#pragma unroll
+    for (int u = 0; u < 16; u++) v[u] = buf[b * P::S + p + P::P * u];
+    pass16<false>(v, tw + P::TB + b, 16);
+    {   // depth 8
+        const bool h = (p >> (P::NS - 1)) & 1;
+        half_swap(v, P::P >> 1, h);
+        const cplx* e = tw + P::TC0 + (t >> (P::NS - 1));
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const cplx w = e[k * P::G0];
+            bf_fwd(v[2 * k], v[8 + 2 * k], w); bf_fwd_i(v[2 * k + 1], v[8 + 2 * k + 1], w);
+        }
+    }
+    if (P::NS > 1) {   // depth 9 (M = 1024)
+        half_swap(v, 1, p & 1);
+        const cplx* e = tw + P::TC1 + t;
+#pragma unroll
+        for (int k = 0; k < 8; k++) bf_fwd(v[k], v[8 + k], e[k * T]);
+    }
+}
+
+// Backward: the exact mirror.  in v[i] = spectrum slot i ; out v[m] = M * z_{t + T m}
+template <int LOGM>
+__device__ __forceinline__ void tree_backward(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id) {
+    typedef TreePlan<LOGM> P;
+    constexpr int T = P::T;
+    const int b = t / P::P, p = t % P::P;
+    if (P::NS > 1) {
+        const cplx* e = tw + P::TC1 + t;
+#pragma unroll
+        for (int k = 0; k < 8; k++) bf_inv(v[k], v[8 + k], e[k * T]);
+        half_swap(v, 1, p & 1);
+    }
+    {
+        const cplx* e = tw + P::TC0 + (t >> (P::NS - 1));
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const cplx w = e[k * P::G0];
+            bf_inv(v[2 * k], v[8 + 2 * k], w); bf_inv_i(v[2 * k + 1], v[8 + 2 * k + 1], w);
+        }
+        half_swap(v, P::P >> 1, (p >> (P::NS - 1)) & 1);
+    }
+    pass16<true>(v, tw + P::TB + b, 16);
+    lanes_sync<T>(bar_id);
+#pragma unroll
+    for (int u = 0; u < 16; u++) buf[b * P::S + p + P::P * u] = v[u];
+    lanes_sync<T>(bar_id);
+#pragma unroll
+    for (int m = 0; m < 16; m++) v[m] = buf[m * P::S + t];
+    pass16<true>(v, tw + P::TA, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// double -> torus, truncation toward zero then wrap, on the FP64 pipe (F2I is full rate there; the
+// integer bit-twiddling form costs ~25 ALU ops, see profiles/microbench_r1.txt).
+//   Torus32: int32_t(int64_t(x))                     cb/spqlios/fft_processor_spqlios.cpp:102
+//   Torus64: significand shifted by the exponent     cb/spqlios/fft_processor_spqlios.cpp:131-142
+//            == trunc(x) mod 2^64.  x - 2^64 rint(x 2^-64) is exact and lies in [-2^63, 2^63]; |x| >= 2^53 is already an
+//            integer, so truncating the remainder equals truncating x.  +2^63 wraps to INT64_MIN like the reference.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t double_to_torus32(double x) { return (int32_t)__double2ll_rz(x); }
+__device__ __forceinline__ int64_t double_to_torus64(double x) {
+    const double q = rint(x * 5.42101086242752217e-20);              // 2^-64
+    const double r = fma(q, -18446744073709551616.0, x);
+    return r >= 9223372036854775808.0 ? (int64_t)0x8000000000000000ull : __double2ll_rz(r);
+}
+
+// (X^a - 1) * P at coefficient j, a in [0, 2N)   (cb/numeric_functions.cpp:304-323)
+template <typename T, int N> __device__ __forceinline__ T rot_minus_one(const T* __restrict__ P, int j, int a) {
+    const int idx = (j - a) & (2 * N - 1);
+    const T r = P[idx & (N - 1)];
+    return (T)(((idx & N) ? (T)0 - r : r) - P[j]);
+}
+
+}  // namespace tfhe_b200

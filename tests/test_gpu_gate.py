@@ -130,7 +130,10 @@ def test_bootstrap_woKS_phase(gate_engine, gate_oracle):
 
 
 def test_blind_rotate_and_extract_testvec(gate_engine, gate_oracle):
-    """tfhe_blindRotateAndExtract_FFT with an arbitrary test polynomial: phase == v[phase index] up to noise."""
+    """tfhe_blindRotateAndExtract_FFT with an arbitrary test polynomial: phase == v[phase index] up to bootstrapping noise.
+    GPU and oracle use different FFT roundings; after the first gadget digit that rounds differently the two accumulators are
+    different encryptions of the same plaintext (bk rows have uniform masks), so their noises are independent samples of
+    the same distribution (sigma ~ 2^24): the phases agree to a few sigma, not to the LSB."""
     g = gate_oracle
     rng = np.random.default_rng(9)
     B = 8
@@ -142,7 +145,7 @@ def test_blind_rotate_and_extract_testvec(gate_engine, gate_oracle):
     torch.cuda.synchronize()
     ref = g.blindRotateAndExtract(v, barb, bara)
     d = _centered(g.phase_N(out.cpu().numpy()) - g.phase_N(ref))
-    assert np.abs(d).max() < 2**22, f"phase differs from the oracle by {np.abs(d).max()}"
+    assert np.abs(d).max() < 2**27.5, f"phase differs from the oracle by {np.abs(d).max()} (> 7 sigma of the difference)"
 
 
 @pytest.mark.parametrize("op", O.GATES)
