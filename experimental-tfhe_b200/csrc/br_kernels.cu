@@ -21,6 +21,8 @@
 // The reference's `if (barai==0) continue` (:350) is kept (group-uniform branch).
 #include "engine.h"
 #include "tree_fft.cuh"
+#include "bk_pipe.cuh"
+#include <cstdlib>
 
 namespace tfhe_b200 {
 
@@ -50,25 +52,40 @@ __device__ __forceinline__ int modswitch32(int32_t x, int log2Msize) {
     return (int)(phase64 >> (64 - log2Msize));
 }
 
+// R[i] += v[i] * bk[i] for the 16 spectrum slots of this lane; bk = one key polynomial staged in shared memory
 template <int LOGM>
-__device__ __forceinline__ void mac_bk(cplx (&R0)[16], cplx (&R1)[16], const cplx (&v)[16], const cplx* __restrict__ bkp) {
-    constexpr int T = TreePlan<LOGM>::T, M = TreePlan<LOGM>::M;
+__device__ __forceinline__ void mac_bk(cplx (&R)[16], const cplx (&v)[16], const cplx* __restrict__ bkp) {
+    constexpr int T = TreePlan<LOGM>::T;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const cplx b0 = __ldg(bkp + i * T);
-        const cplx b1 = __ldg(bkp + M + i * T);
-        cfma(R0[i], v[i], b0);
-        cfma(R1[i], v[i], b1);
-    }
+    for (int i = 0; i < 16; i++) cfma(R[i], v[i], bkp[i * T]);
 }
 
-// One CMUX: ACC <- ACC + BK_i (x) ((X^a - 1) ACC).   acc: shared [2][N].  bk: [2l][2][M] spectra (scaled 2/N).
+// forward transform of one digit polynomial + its two multiply-accumulates, with the key polynomials requested ahead:
+// BK[p][1] -> kb1 now, BK[p][0] -> the transpose buffer as soon as the transpose is over (bk_pipe.cuh)
+template <int LOGM>
+__device__ __forceinline__ void forward_and_mac(cplx (&v)[16], cplx (&R0)[16], cplx (&R1)[16], const cplx* __restrict__ bkp,
+                                                cplx* __restrict__ buf, BkSlot& s0, BkSlot& s1,
+                                                const cplx* __restrict__ tw, const int t, const int bar_id) {
+    typedef TreePlan<LOGM> P;
+    constexpr uint32_t POLY = P::M * sizeof(cplx);
+    lanes_sync<P::T>(bar_id);                                   // previous reads of kb1 are over
+    if (t == 0) s1.request(bkp + P::M, POLY);
+    tree_forward_a<LOGM>(v, buf, tw, t, bar_id);                // ends with a sync: nobody reads buf any more
+    if (t == 0) s0.request(bkp, POLY);
+    tree_forward_b<LOGM>(v, tw, t);
+    s0.wait();
+    mac_bk<LOGM>(R0, v, reinterpret_cast<const cplx*>(s0.dst) + t);
+    s1.wait();
+    mac_bk<LOGM>(R1, v, reinterpret_cast<const cplx*>(s1.dst) + t);
+}
+
+// One CMUX: ACC <- ACC + BK_i (x) ((X^a - 1) ACC).   acc: shared [2][N].  bk: BK_i = [2l][2][M] spectra (scaled 2/N).
 // LT == 2: both gadget digits of a coefficient come from one accumulator read (the second is parked, packed, in a
 // lane-private shared-memory word); otherwise the accumulator is re-read per level.
 template <int LOGM, typename Torus, int LT>
 __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, const cplx* __restrict__ bk,
                                           const int l, const int Bgbit, cplx* __restrict__ buf, uint32_t* __restrict__ pk,
-                                          const cplx* __restrict__ tw, const int t, const int bar_id) {
+                                          BkSlot& s0, BkSlot& s1, const cplx* __restrict__ tw, const int t, const int bar_id) {
     typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
     constexpr int M = P::M, N = P::N, T = P::T, W = TorusTraits<Torus>::W;
@@ -83,44 +100,54 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
 #pragma unroll 1
     for (int q = 0; q < 2; q++) {
         const Torus* __restrict__ aq = acc + q * N;
+        int aa = a;
+        asm volatile("" : "+r"(aa));      // keep the 32 rotated addresses from being hoisted out of the q loop (and spilled)
         if (LT == 2) {
-            cplx v[16];
             const int sh0 = W - Bgbit, sh1 = W - 2 * Bgbit;
+#pragma unroll 1
+            for (int lev = 0; lev < 2; lev++) {
+                cplx v[16];
+                if (lev == 0) {
+                    int a2 = aa;
+                    asm volatile("" : "+r"(a2));      // ... nor out of the level loop
 #pragma unroll
-            for (int m = 0; m < 16; m++) {
-                const int j = t + T * m;
-                const U ure = (U)rot_minus_one<Torus, N>(aq, j, a) + offset;
-                const U uim = (U)rot_minus_one<Torus, N>(aq, j + M, a) + offset;
-                v[m] = make_double2((double)((int)((uint32_t)(ure >> sh0) & mask) - half),
-                                    (double)((int)((uint32_t)(uim >> sh0) & mask) - half));
-                const uint32_t d1r = (uint32_t)((int)((uint32_t)(ure >> sh1) & mask) - half);
-                const uint32_t d1i = (uint32_t)((int)((uint32_t)(uim >> sh1) & mask) - half);
-                pk[m * T + t] = (d1r & 0xFFFFu) | (d1i << 16);     // lane-private slot, parked in shared memory
-            }
-            tree_forward<LOGM>(v, buf, tw, t, bar_id);
-            mac_bk<LOGM>(R0, R1, v, bk + (size_t)((q * 2 + 0) * 2) * M + t);
+                    for (int m = 0; m < 16; m++) {
+                        const int j = t + T * m;
+                        const U ure = (U)rot_minus_one<Torus, N>(aq, j, a2) + offset;
+                        const U uim = (U)rot_minus_one<Torus, N>(aq, j + M, a2) + offset;
+                        v[m] = make_double2((double)((int)((uint32_t)(ure >> sh0) & mask) - half),
+                                            (double)((int)((uint32_t)(uim >> sh0) & mask) - half));
+                        const uint32_t d1r = (uint32_t)((int)((uint32_t)(ure >> sh1) & mask) - half);
+                        const uint32_t d1i = (uint32_t)((int)((uint32_t)(uim >> sh1) & mask) - half);
+                        pk[m * T + t] = (d1r & 0xFFFFu) | (d1i << 16);     // lane-private slot, parked in shared memory
+                        if ((m & 3) == 3) asm volatile("" ::: "memory");   // cap the LDS results in flight: R0/R1 own 128 registers
+                    }
+                } else {
 #pragma unroll
-            for (int m = 0; m < 16; m++) {
-                const uint32_t w1 = pk[m * T + t];
-                v[m] = make_double2((double)((int)(w1 << 16) >> 16), (double)((int)w1 >> 16));
+                    for (int m = 0; m < 16; m++) {
+                        const uint32_t w1 = pk[m * T + t];
+                        v[m] = make_double2((double)((int)(w1 << 16) >> 16), (double)((int)w1 >> 16));
+                    }
+                }
+                forward_and_mac<LOGM>(v, R0, R1, bk + (size_t)((q * 2 + lev) * 2) * M, buf, s0, s1, tw, t, bar_id);
             }
-            tree_forward<LOGM>(v, buf, tw, t, bar_id);
-            mac_bk<LOGM>(R0, R1, v, bk + (size_t)((q * 2 + 1) * 2) * M + t);
         } else {
 #pragma unroll 1
             for (int lev = 0; lev < l; lev++) {
                 const int sh = W - (lev + 1) * Bgbit;
                 cplx v[16];
+                int a2 = aa;
+                asm volatile("" : "+r"(a2));          // ... nor out of the level loop
 #pragma unroll
                 for (int m = 0; m < 16; m++) {
                     const int j = t + T * m;
-                    const U ure = (U)rot_minus_one<Torus, N>(aq, j, a) + offset;
-                    const U uim = (U)rot_minus_one<Torus, N>(aq, j + M, a) + offset;
+                    const U ure = (U)rot_minus_one<Torus, N>(aq, j, a2) + offset;
+                    const U uim = (U)rot_minus_one<Torus, N>(aq, j + M, a2) + offset;
                     v[m] = make_double2((double)((int)((uint32_t)(ure >> sh) & mask) - half),
                                         (double)((int)((uint32_t)(uim >> sh) & mask) - half));
+                    if ((m & 3) == 3) asm volatile("" ::: "memory");
                 }
-                tree_forward<LOGM>(v, buf, tw, t, bar_id);
-                mac_bk<LOGM>(R0, R1, v, bk + (size_t)((q * l + lev) * 2) * M + t);
+                forward_and_mac<LOGM>(v, R0, R1, bk + (size_t)((q * l + lev) * 2) * M, buf, s0, s1, tw, t, bar_id);
             }
         }
     }
@@ -142,74 +169,79 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
     lanes_sync<T>(bar_id);      // accumulator writes visible before the next step's rotated reads
 }
 
-template <int LOGM, typename Torus, int GROUPS> struct BRSmem {
+template <int LOGM, typename Torus, int GROUPS, int LT> struct BRSmem {
     typedef TreePlan<LOGM> P;
-    static constexpr int NPAD = 1024;   // room for bara (n <= 1023, plus b)
-    static constexpr size_t TW_BYTES = sizeof(cplx) * ((P::TW_TOTAL + 1) & ~1);
-    static constexpr size_t GROUP_BYTES = sizeof(cplx) * P::BUF + sizeof(Torus) * 2 * P::N + sizeof(int32_t) * NPAD + sizeof(uint32_t) * 16 * P::T;
+    static constexpr size_t TW_BYTES = sizeof(cplx) * ((P::TW_TOTAL + 7) & ~7);        // 128-byte multiple
+    static constexpr size_t CTRL_BYTES = 128;                                          // two mbarriers
+    static constexpr size_t BUF_BYTES = (sizeof(cplx) * P::BUF + 127) & ~(size_t)127;  // transpose buffer, also lands BK[p][0]
+    static constexpr size_t ACC_BYTES = sizeof(Torus) * 2 * P::N;
+    static constexpr size_t KB1_BYTES = sizeof(cplx) * P::M;                           // lands BK[p][1]
+    static constexpr size_t PK_BYTES = LT == 2 ? sizeof(uint32_t) * 16 * P::T : 0;
+    static constexpr size_t GROUP_BYTES = CTRL_BYTES + BUF_BYTES + ACC_BYTES + KB1_BYTES + PK_BYTES;
     static constexpr size_t TOTAL = TW_BYTES + GROUPS * GROUP_BYTES;
+    static_assert(sizeof(cplx) * P::BUF >= KB1_BYTES, "transpose buffer must hold one key polynomial");
+    static_assert(TOTAL <= 232448, "shared memory budget (227 KB) exceeded");
 };
+
+// rotation amount i of sample ct (i == n: the b part), straight from the kernel's inputs -- nothing is staged in shared memory
+template <int LOGM, typename Torus>
+__device__ __forceinline__ int fetch_bara(const BRArgs& A, const int ct, const int i) {
+    const int n = A.n;
+    if (A.mode == BR_LWE) {
+        if (sizeof(Torus) == 4) {
+            // tfhe_bootstrap_woKS_FFT :416-419 on x = (0,cconst) + ka*xa + kb*xb  (boots* linear part)
+            uint32_t x = (uint32_t)A.ka * (uint32_t)__ldg(A.xa + (size_t)ct * (n + 1) + i);
+            if (A.xb) x += (uint32_t)A.kb * (uint32_t)__ldg(A.xb + (size_t)ct * (n + 1) + i);
+            if (i == n) x += (uint32_t)A.cconst;
+            return modswitch32((int32_t)x, LOGM + 2);
+        }
+        // circuitBootstrapWoKS: abar[n0+1] already mod-switched (cb/poc_CircuitBootstrapping.cpp:542,581)
+        return __ldg(A.bara + (size_t)ct * (n + 1) + i);
+    }
+    if (i == n) return A.mode == BR_TESTVEC ? __ldg(A.barb + ct) : 0;
+    return __ldg(A.bara + (size_t)ct * n + i);
+}
 
 template <int LOGM, typename Torus, int GROUPS, int LT>
 __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_kernel(const BRArgs A) {
     typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
-    typedef BRSmem<LOGM, Torus, GROUPS> S;
+    typedef BRSmem<LOGM, Torus, GROUPS, LT> S;
     constexpr int M = P::M, N = P::N, T = P::T;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* tw = reinterpret_cast<cplx*>(smem_raw);
-    for (int i = threadIdx.x; i < P::TW_TOTAL; i += GROUPS * T) tw[i] = A.tw[i];
-    __syncthreads();
-
     const int g = threadIdx.x / T, t = threadIdx.x % T;
     const int bar_id = 1 + g;
     unsigned char* gbase = smem_raw + S::TW_BYTES + (size_t)g * S::GROUP_BYTES;
-    cplx* buf = reinterpret_cast<cplx*>(gbase);
-    Torus* acc = reinterpret_cast<Torus*>(gbase + sizeof(cplx) * P::BUF);
-    int32_t* bara = reinterpret_cast<int32_t*>(gbase + sizeof(cplx) * P::BUF + sizeof(Torus) * 2 * N);
-    uint32_t* pk = reinterpret_cast<uint32_t*>(bara + S::NPAD);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gbase);
+    cplx* buf = reinterpret_cast<cplx*>(gbase + S::CTRL_BYTES);
+    Torus* acc = reinterpret_cast<Torus*>(gbase + S::CTRL_BYTES + S::BUF_BYTES);
+    unsigned char* kb1 = gbase + S::CTRL_BYTES + S::BUF_BYTES + S::ACC_BYTES;
+    uint32_t* pk = reinterpret_cast<uint32_t*>(kb1 + S::KB1_BYTES);
+
+    for (int i = threadIdx.x; i < P::TW_TOTAL; i += GROUPS * T) tw[i] = A.tw[i];
+    if (t == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    BkSlot s0{&bars[0], reinterpret_cast<unsigned char*>(buf), 0u};
+    BkSlot s1{&bars[1], kb1, 0u};
 
     // unit = (sample, test-vector index); n_mu > 1 only on the circuit-bootstrap path
     const int n_mu = A.n_mu > 0 ? A.n_mu : 1;
     const long unit = (long)blockIdx.x * GROUPS + g;
-    if (unit >= (long)A.count * n_mu) return;          // whole group leaves; its barriers are private to it
+    if (unit >= (long)A.count * n_mu) return;          // whole group leaves; nothing is shared between groups
     const int ct = (int)(unit / n_mu), w = (int)(unit % n_mu);
     const int n = A.n;
+    const int l = LT == 2 ? 2 : A.l;
 
-    // ---- rotation amounts and the initial accumulator
-    int barb = 0;
+    // ---- the initial accumulator
     Torus mu = (Torus)A.mu;
-    if (A.mode == BR_LWE) {
-        if (sizeof(Torus) == 4) {
-            // tfhe_bootstrap_woKS_FFT :416-419 on x = (0,cconst) + ka*xa + kb*xb  (boots* linear part)
-            const int32_t* xa = A.xa + (size_t)ct * (n + 1);
-            const int32_t* xb = A.xb ? A.xb + (size_t)ct * (n + 1) : nullptr;
-            for (int i = t; i <= n; i += T) {
-                uint32_t x = (uint32_t)A.ka * (uint32_t)xa[i];
-                if (xb) x += (uint32_t)A.kb * (uint32_t)xb[i];
-                if (i == n) x += (uint32_t)A.cconst;
-                bara[i] = modswitch32((int32_t)x, LOGM + 2);
-            }
-        } else {
-            // circuitBootstrapWoKS: abar[n0+1] already mod-switched (cb/poc_CircuitBootstrapping.cpp:542,581)
-            const int32_t* ab = A.bara + (size_t)ct * (n + 1);
-            for (int i = t; i <= n; i += T) bara[i] = ab[i];
-            if (A.mu_bgbit > 0) mu = (Torus)(1ull << (64 - (w + 1) * A.mu_bgbit));   // mu_w, poc:846
-        }
-        lanes_sync<T>(bar_id);
-        barb = bara[n];
-    } else {
-        const int32_t* ab = A.bara + (size_t)ct * n;
-        for (int i = t; i < n; i += T) bara[i] = ab[i];
-        if (A.mode == BR_TESTVEC) barb = A.barb[ct];
-        lanes_sync<T>(bar_id);
-    }
-
+    if (sizeof(Torus) == 8 && A.mode == BR_LWE && A.mu_bgbit > 0) mu = (Torus)(1ull << (64 - (w + 1) * A.mu_bgbit));   // mu_w, poc:846
     if (A.mode == BR_ACCUM) {
         const Torus* src = reinterpret_cast<const Torus*>(A.accum) + (size_t)ct * 2 * N;
         for (int j = t; j < 2 * N; j += T) acc[j] = src[j];
     } else {
         // testvectbis = X^(2N - barb) * v  (cb/lwe_functions.cpp:385; defect D3 of the PoC corrected the same way)
+        const int barb = fetch_bara<LOGM, Torus>(A, ct, n);
         const int rot = (2 * N - barb) & (2 * N - 1);
         const Torus* v = reinterpret_cast<const Torus*>(A.v);
         for (int j = t; j < N; j += T) {
@@ -225,12 +257,15 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
     }
     lanes_sync<T>(bar_id);
 
-    // ---- n CMUX steps (tfhe_blindRotate_FFT :348-354)
-    const size_t bk_stride = (size_t)2 * A.l * 2 * M;
+    // ---- n CMUX steps (tfhe_blindRotate_FFT :348-354); a step with bara == 0 is skipped like the reference does (:350).
+    // The next rotation amount is fetched one step ahead.
+    const size_t bk_stride = (size_t)2 * l * 2 * M;
+    int a_next = fetch_bara<LOGM, Torus>(A, ct, 0);
     for (int i = 0; i < n; i++) {
-        const int a = bara[i];
+        const int a = a_next;
+        if (i + 1 < n) a_next = fetch_bara<LOGM, Torus>(A, ct, i + 1);
         if (a == 0) continue;
-        cmux_step<LOGM, Torus, LT>(acc, a, A.bkfft + (size_t)i * bk_stride, LT == 2 ? 2 : A.l, A.Bgbit, buf, pk, tw, t, bar_id);
+        cmux_step<LOGM, Torus, LT>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, pk, s0, s1, tw, t, bar_id);
     }
 
     // ---- epilogue
@@ -254,7 +289,7 @@ constexpr int G32 = 8, G64 = 3;     // accumulators per CTA: 8 warps (N=1024) / 
 
 template <int LOGM, typename Torus, int GROUPS, int LT> static cudaError_t br_attr() {
     return cudaFuncSetAttribute(blind_rotate_kernel<LOGM, Torus, GROUPS, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)BRSmem<LOGM, Torus, GROUPS>::TOTAL);
+                                (int)BRSmem<LOGM, Torus, GROUPS, LT>::TOTAL);
 }
 cudaError_t blind_rotate_init() {
     cudaError_t e;
@@ -269,9 +304,11 @@ cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
     if (!g_inited) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
     if (a.count <= 0) return cudaSuccess;
     const int grid = (a.count + G32 - 1) / G32;
-    const size_t smem = BRSmem<9, int32_t, G32>::TOTAL;
-    if (a.l == 2) blind_rotate_kernel<9, int32_t, G32, 2><<<grid, G32 * TreePlan<9>::T, smem, s>>>(a);
-    else          blind_rotate_kernel<9, int32_t, G32, 0><<<grid, G32 * TreePlan<9>::T, smem, s>>>(a);
+    static const bool force_generic = getenv("TFHE_B200_GENERIC_L") != nullptr;   // development knob
+    if (a.l == 2 && !force_generic)
+        blind_rotate_kernel<9, int32_t, G32, 2><<<grid, G32 * TreePlan<9>::T, BRSmem<9, int32_t, G32, 2>::TOTAL, s>>>(a);
+    else
+        blind_rotate_kernel<9, int32_t, G32, 0><<<grid, G32 * TreePlan<9>::T, BRSmem<9, int32_t, G32, 0>::TOTAL, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
@@ -279,7 +316,7 @@ cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
     if (a.count <= 0) return cudaSuccess;
     const long units = (long)a.count * (a.n_mu > 0 ? a.n_mu : 1);
     const int grid = (int)((units + G64 - 1) / G64);
-    blind_rotate_kernel<10, int64_t, G64, 0><<<grid, G64 * TreePlan<10>::T, BRSmem<10, int64_t, G64>::TOTAL, s>>>(a);
+    blind_rotate_kernel<10, int64_t, G64, 0><<<grid, G64 * TreePlan<10>::T, BRSmem<10, int64_t, G64, 0>::TOTAL, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -150,18 +150,26 @@ __device__ __forceinline__ void half_swap(cplx (&v)[16], const int mask, const b
 
 // Forward: in  v[m] = z_{t + T m}  (t = lane in [0,T), natural coefficient order, stride T)
 //          out v[i] = spectrum slot i of this lane (leaf order, private)
+// Split in two so the caller can reuse the transpose buffer between the halves (after part A nobody reads buf any more).
 template <int LOGM>
-__device__ __forceinline__ void tree_forward(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id) {
+__device__ __forceinline__ void tree_forward_a(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id) {
     typedef TreePlan<LOGM> P;
     constexpr int T = P::T;
     pass16<false>(v, tw + P::TA, 1);
-    lanes_sync<T>(bar_id);                                   // WAR: previous transform's reads of buf
+    lanes_sync<T>(bar_id);                                   // WAR: earlier reads of buf
 #pragma unroll
     for (int m = 0; m < 16; m++) buf[m * P::S + t] = v[m];
     lanes_sync<T>(bar_id);
     const int b = t / P::P, p = t % P::P;
 #pragma unroll
     for (int u = 0; u < 16; u++) v[u] = buf[b * P::S + p + P::P * u];
+    lanes_sync<T>(bar_id);                                   // every lane is done with buf
+}
+template <int LOGM>
+__device__ __forceinline__ void tree_forward_b(cplx (&v)[16], const cplx* __restrict__ tw, const int t) {
+    typedef TreePlan<LOGM> P;
+    constexpr int T = P::T;
+    const int b = t / P::P, p = t % P::P;
     pass16<false>(v, tw + P::TB + b, 16);
     {   // depth 8
         const bool h = (p >> (P::NS - 1)) & 1;
@@ -179,6 +187,11 @@ __device__ __forceinline__ void tree_forward(cplx (&v)[16], cplx* __restrict__ b
 #pragma unroll
         for (int k = 0; k < 8; k++) bf_fwd(v[k], v[8 + k], e[k * T]);
     }
+}
+template <int LOGM>
+__device__ __forceinline__ void tree_forward(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id) {
+    tree_forward_a<LOGM>(v, buf, tw, t, bar_id);
+    tree_forward_b<LOGM>(v, tw, t);
 }
 
 // Backward: the exact mirror.  in v[i] = spectrum slot i ; out v[m] = M * z_{t + T m}
