@@ -304,8 +304,10 @@ cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
     if (!g_inited) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
     if (a.count <= 0) return cudaSuccess;
     const int grid = (a.count + G32 - 1) / G32;
-    static const bool force_generic = getenv("TFHE_B200_GENERIC_L") != nullptr;   // development knob
-    if (a.l == 2 && !force_generic)
+    // The packed two-digit path (LT = 2) saves one accumulator re-read per CMUX but currently costs 80 B of spills;
+    // measured 145k vs 158k bootstraps/s (profiles/r1_notes.md), so the re-read path is the default.
+    static const bool use_packed = getenv("TFHE_B200_PACKED_DIGITS") != nullptr;   // development knob
+    if (a.l == 2 && use_packed)
         blind_rotate_kernel<9, int32_t, G32, 2><<<grid, G32 * TreePlan<9>::T, BRSmem<9, int32_t, G32, 2>::TOTAL, s>>>(a);
     else
         blind_rotate_kernel<9, int32_t, G32, 0><<<grid, G32 * TreePlan<9>::T, BRSmem<9, int32_t, G32, 0>::TOTAL, s>>>(a);
