@@ -52,40 +52,83 @@ __device__ __forceinline__ int modswitch32(int32_t x, int log2Msize) {
     return (int)(phase64 >> (64 - log2Msize));
 }
 
-// R[i] += v[i] * bk[i] for the 16 spectrum slots of this lane; bk = one key polynomial staged in shared memory
-template <int LOGM>
-__device__ __forceinline__ void mac_bk(cplx (&R)[16], const cplx (&v)[16], const cplx* __restrict__ bkp) {
-    constexpr int T = TreePlan<LOGM>::T;
+// ---------------------------------------------------------------------------------------------
+// Spectral accumulators in TENSOR MEMORY.  The two accumulators of a CMUX (2 x 16 complex doubles per lane = 128 32-bit
+// registers) would pin half the register file and cap the SM at 8 warps.  They live in TMEM instead: lane i of warp w
+// owns TMEM lane 32*(w%4)+i, columns [(w/4)*128, +128) -- R0 in the first 64 columns, R1 in the next 64 -- and are
+// read-modify-written 16 columns at a time around each multiply-accumulate (tcgen05.ld/st.32x32b, SASS LDTM/STTM;
+// no MMA is involved).  profiles/tmem_probe_r1.txt: an accumulator round trip sustains ~445 B/clk/SM next to LDS and DFMA.
+// ---------------------------------------------------------------------------------------------
+#define TFHE_TLD16(r, addr)                                                                                                    \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"       \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                     \
+                 : "r"(addr) : "memory")
+#define TFHE_TST16(r, addr)                                                                                                    \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"       \
+                 ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), \
+                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(addr) : "memory")
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// R (in TMEM at taddr, 64 columns) (+)= v (.) b over this lane's 16 spectrum slots; FIRST: plain product, nothing to load.
+// b(i) yields the key value of slot i (shared memory or registers).
+template <bool FIRST, typename BFn>
+__device__ __forceinline__ void mac_tmem(const uint32_t taddr, const cplx (&v)[16], BFn b) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) cfma(R[i], v[i], bkp[i * T]);
+    for (int c = 0; c < 4; c++) {
+        uint32_t r[16];
+        if (!FIRST) { TFHE_TLD16(r, taddr + 16 * c); tmem_wait_ld(); }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            cplx R = FIRST ? make_double2(0.0, 0.0)
+                           : make_double2(__hiloint2double((int)r[4 * i + 1], (int)r[4 * i]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]));
+            cfma(R, v[4 * c + i], b(4 * c + i));
+            r[4 * i] = (uint32_t)__double2loint(R.x); r[4 * i + 1] = (uint32_t)__double2hiint(R.x);
+            r[4 * i + 2] = (uint32_t)__double2loint(R.y); r[4 * i + 3] = (uint32_t)__double2hiint(R.y);
+        }
+        TFHE_TST16(r, taddr + 16 * c);
+    }
+    tmem_wait_st();
+}
+__device__ __forceinline__ void load_tmem(cplx (&R)[16], const uint32_t taddr) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        uint32_t r[16];
+        TFHE_TLD16(r, taddr + 16 * c);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            R[4 * c + i] = make_double2(__hiloint2double((int)r[4 * i + 1], (int)r[4 * i]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]));
+    }
 }
 
-// forward transform of one digit polynomial + its two multiply-accumulates, with the key polynomials requested ahead:
-// BK[p][1] -> kb1 now, BK[p][0] -> the transpose buffer as soon as the transpose is over (bk_pipe.cuh)
-template <int LOGM>
-__device__ __forceinline__ void forward_and_mac(cplx (&v)[16], cplx (&R0)[16], cplx (&R1)[16], const cplx* __restrict__ bkp,
-                                                cplx* __restrict__ buf, BkSlot& s0, BkSlot& s1,
+// forward transform of one digit polynomial + its two multiply-accumulates.  Key polynomial BK[p][0] lands in the transpose
+// buffer by TMA as soon as the transpose is over (bk_pipe.cuh); BK[p][1] is prefetched into registers (the accumulators no
+// longer occupy them) while the second half of the transform runs.
+template <int LOGM, bool FIRST>
+__device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t tacc, const cplx* __restrict__ bkp,
+                                                cplx* __restrict__ buf, BkSlot& s0,
                                                 const cplx* __restrict__ tw, const int t, const int bar_id) {
     typedef TreePlan<LOGM> P;
     constexpr uint32_t POLY = P::M * sizeof(cplx);
-    lanes_sync<P::T>(bar_id);                                   // previous reads of kb1 are over
-    if (t == 0) s1.request(bkp + P::M, POLY);
     tree_forward_a<LOGM>(v, buf, tw, t, bar_id);                // ends with a sync: nobody reads buf any more
     if (t == 0) s0.request(bkp, POLY);
+    cplx b1[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) b1[i] = __ldg(bkp + P::M + i * P::T + t);
     tree_forward_b<LOGM>(v, tw, t);
     s0.wait();
-    mac_bk<LOGM>(R0, v, reinterpret_cast<const cplx*>(s0.dst) + t);
-    s1.wait();
-    mac_bk<LOGM>(R1, v, reinterpret_cast<const cplx*>(s1.dst) + t);
+    const cplx* b0 = reinterpret_cast<const cplx*>(s0.dst) + t;
+    mac_tmem<FIRST>(tacc, v, [&](int i) { return b0[i * P::T]; });
+    mac_tmem<FIRST>(tacc + 64, v, [&](int i) { return b1[i]; });
 }
 
 // One CMUX: ACC <- ACC + BK_i (x) ((X^a - 1) ACC).   acc: shared [2][N].  bk: BK_i = [2l][2][M] spectra (scaled 2/N).
-// LT == 2: both gadget digits of a coefficient come from one accumulator read (the second is parked, packed, in a
-// lane-private shared-memory word); otherwise the accumulator is re-read per level.
-template <int LOGM, typename Torus, int LT>
+template <int LOGM, typename Torus>
 __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, const cplx* __restrict__ bk,
-                                          const int l, const int Bgbit, cplx* __restrict__ buf, uint32_t* __restrict__ pk,
-                                          BkSlot& s0, BkSlot& s1, const cplx* __restrict__ tw, const int t, const int bar_id) {
+                                          const int l, const int Bgbit, cplx* __restrict__ buf, const uint32_t tacc,
+                                          BkSlot& s0, const cplx* __restrict__ tw, const int t, const int bar_id) {
     typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
     constexpr int M = P::M, N = P::N, T = P::T, W = TorusTraits<Torus>::W;
@@ -93,94 +136,63 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
     const uint32_t mask = (1u << Bgbit) - 1u;
     const int half = 1 << (Bgbit - 1);
 
-    cplx R0[16], R1[16];
-#pragma unroll
-    for (int e = 0; e < 16; e++) { R0[e] = make_double2(0.0, 0.0); R1[e] = make_double2(0.0, 0.0); }
-
 #pragma unroll 1
-    for (int q = 0; q < 2; q++) {
+    for (int p = 0; p < 2 * l; p++) {
+        const int q = p >= l, lev = p - q * l;
         const Torus* __restrict__ aq = acc + q * N;
-        int aa = a;
-        asm volatile("" : "+r"(aa));      // keep the 32 rotated addresses from being hoisted out of the q loop (and spilled)
-        if (LT == 2) {
-            const int sh0 = W - Bgbit, sh1 = W - 2 * Bgbit;
-#pragma unroll 1
-            for (int lev = 0; lev < 2; lev++) {
-                cplx v[16];
-                if (lev == 0) {
-                    int a2 = aa;
-                    asm volatile("" : "+r"(a2));      // ... nor out of the level loop
+        const int sh = W - (lev + 1) * Bgbit;
+        cplx v[16];
+        int a2 = a;
+        asm volatile("" : "+r"(a2));          // keep the 32 rotated addresses from being hoisted out of the loop
 #pragma unroll
-                    for (int m = 0; m < 16; m++) {
-                        const int j = t + T * m;
-                        const U ure = (U)rot_minus_one<Torus, N>(aq, j, a2) + offset;
-                        const U uim = (U)rot_minus_one<Torus, N>(aq, j + M, a2) + offset;
-                        v[m] = make_double2((double)((int)((uint32_t)(ure >> sh0) & mask) - half),
-                                            (double)((int)((uint32_t)(uim >> sh0) & mask) - half));
-                        const uint32_t d1r = (uint32_t)((int)((uint32_t)(ure >> sh1) & mask) - half);
-                        const uint32_t d1i = (uint32_t)((int)((uint32_t)(uim >> sh1) & mask) - half);
-                        pk[m * T + t] = (d1r & 0xFFFFu) | (d1i << 16);     // lane-private slot, parked in shared memory
-                        if ((m & 3) == 3) asm volatile("" ::: "memory");   // cap the LDS results in flight: R0/R1 own 128 registers
-                    }
-                } else {
-#pragma unroll
-                    for (int m = 0; m < 16; m++) {
-                        const uint32_t w1 = pk[m * T + t];
-                        v[m] = make_double2((double)((int)(w1 << 16) >> 16), (double)((int)w1 >> 16));
-                    }
-                }
-                forward_and_mac<LOGM>(v, R0, R1, bk + (size_t)((q * 2 + lev) * 2) * M, buf, s0, s1, tw, t, bar_id);
-            }
-        } else {
-#pragma unroll 1
-            for (int lev = 0; lev < l; lev++) {
-                const int sh = W - (lev + 1) * Bgbit;
-                cplx v[16];
-                int a2 = aa;
-                asm volatile("" : "+r"(a2));          // ... nor out of the level loop
-#pragma unroll
-                for (int m = 0; m < 16; m++) {
-                    const int j = t + T * m;
-                    const U ure = (U)rot_minus_one<Torus, N>(aq, j, a2) + offset;
-                    const U uim = (U)rot_minus_one<Torus, N>(aq, j + M, a2) + offset;
-                    v[m] = make_double2((double)((int)((uint32_t)(ure >> sh) & mask) - half),
-                                        (double)((int)((uint32_t)(uim >> sh) & mask) - half));
-                    if ((m & 3) == 3) asm volatile("" ::: "memory");
-                }
-                forward_and_mac<LOGM>(v, R0, R1, bk + (size_t)((q * l + lev) * 2) * M, buf, s0, s1, tw, t, bar_id);
-            }
+        for (int m = 0; m < 16; m++) {
+            const int j = t + T * m;
+            const U ure = (U)rot_minus_one<Torus, N>(aq, j, a2) + offset;
+            const U uim = (U)rot_minus_one<Torus, N>(aq, j + M, a2) + offset;
+            v[m] = make_double2((double)((int)((uint32_t)(ure >> sh) & mask) - half),
+                                (double)((int)((uint32_t)(uim >> sh) & mask) - half));
         }
+        if (p == 0) forward_and_mac<LOGM, true>(v, tacc, bk, buf, s0, tw, t, bar_id);
+        else        forward_and_mac<LOGM, false>(v, tacc, bk + (size_t)(p * 2) * M, buf, s0, tw, t, bar_id);
     }
     // every lane has finished reading the accumulator once it passes the first sync inside tree_backward
-    tree_backward<LOGM>(R0, buf, tw, t, bar_id);
+    {
+        cplx R[16];
+        load_tmem(R, tacc);
+        tree_backward<LOGM>(R, buf, tw, t, bar_id);
 #pragma unroll
-    for (int m = 0; m < 16; m++) {
-        const int j = t + T * m;
-        acc[j] = (Torus)((U)acc[j] + (U)to_torus(R0[m].x, (Torus)0));
-        acc[j + M] = (Torus)((U)acc[j + M] + (U)to_torus(R0[m].y, (Torus)0));
+        for (int m = 0; m < 16; m++) {
+            const int j = t + T * m;
+            acc[j] = (Torus)((U)acc[j] + (U)to_torus(R[m].x, (Torus)0));
+            acc[j + M] = (Torus)((U)acc[j + M] + (U)to_torus(R[m].y, (Torus)0));
+        }
     }
-    tree_backward<LOGM>(R1, buf, tw, t, bar_id);
+    {
+        cplx R[16];
+        load_tmem(R, tacc + 64);
+        tree_backward<LOGM>(R, buf, tw, t, bar_id);
 #pragma unroll
-    for (int m = 0; m < 16; m++) {
-        const int j = t + T * m;
-        acc[N + j] = (Torus)((U)acc[N + j] + (U)to_torus(R1[m].x, (Torus)0));
-        acc[N + j + M] = (Torus)((U)acc[N + j + M] + (U)to_torus(R1[m].y, (Torus)0));
+        for (int m = 0; m < 16; m++) {
+            const int j = t + T * m;
+            acc[N + j] = (Torus)((U)acc[N + j] + (U)to_torus(R[m].x, (Torus)0));
+            acc[N + j + M] = (Torus)((U)acc[N + j + M] + (U)to_torus(R[m].y, (Torus)0));
+        }
     }
     lanes_sync<T>(bar_id);      // accumulator writes visible before the next step's rotated reads
 }
 
-template <int LOGM, typename Torus, int GROUPS, int LT> struct BRSmem {
+template <int LOGM, typename Torus, int GROUPS> struct BRSmem {
     typedef TreePlan<LOGM> P;
     static constexpr size_t TW_BYTES = sizeof(cplx) * ((P::TW_TOTAL + 7) & ~7);        // 128-byte multiple
-    static constexpr size_t CTRL_BYTES = 128;                                          // two mbarriers
+    static constexpr size_t CTRL_BYTES = 128;                                          // mbarrier (+ TMEM base in group 0)
     static constexpr size_t BUF_BYTES = (sizeof(cplx) * P::BUF + 127) & ~(size_t)127;  // transpose buffer, also lands BK[p][0]
     static constexpr size_t ACC_BYTES = sizeof(Torus) * 2 * P::N;
-    static constexpr size_t KB1_BYTES = sizeof(cplx) * P::M;                           // lands BK[p][1]
-    static constexpr size_t PK_BYTES = LT == 2 ? sizeof(uint32_t) * 16 * P::T : 0;
-    static constexpr size_t GROUP_BYTES = CTRL_BYTES + BUF_BYTES + ACC_BYTES + KB1_BYTES + PK_BYTES;
+    static constexpr size_t GROUP_BYTES = CTRL_BYTES + BUF_BYTES + ACC_BYTES;
     static constexpr size_t TOTAL = TW_BYTES + GROUPS * GROUP_BYTES;
-    static_assert(sizeof(cplx) * P::BUF >= KB1_BYTES, "transpose buffer must hold one key polynomial");
+    static constexpr int WARPS = GROUPS * P::T / 32;
+    static_assert(sizeof(cplx) * P::BUF >= sizeof(cplx) * P::M, "transpose buffer must hold one key polynomial");
     static_assert(TOTAL <= 232448, "shared memory budget (227 KB) exceeded");
+    static_assert((WARPS + 3) / 4 * 128 <= 512, "tensor memory: 128 columns per warp, 4 lane quarters");
 };
 
 // rotation amount i of sample ct (i == n: the b part), straight from the kernel's inputs -- nothing is staged in shared memory
@@ -202,100 +214,109 @@ __device__ __forceinline__ int fetch_bara(const BRArgs& A, const int ct, const i
     return __ldg(A.bara + (size_t)ct * n + i);
 }
 
-template <int LOGM, typename Torus, int GROUPS, int LT>
+template <int LOGM, typename Torus, int GROUPS>
 __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_kernel(const BRArgs A) {
     typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
-    typedef BRSmem<LOGM, Torus, GROUPS, LT> S;
+    typedef BRSmem<LOGM, Torus, GROUPS> S;
     constexpr int M = P::M, N = P::N, T = P::T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* tw = reinterpret_cast<cplx*>(smem_raw);
-    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    const int g = threadIdx.x / T, t = threadIdx.x % T, warp = threadIdx.x >> 5;
     const int bar_id = 1 + g;
     unsigned char* gbase = smem_raw + S::TW_BYTES + (size_t)g * S::GROUP_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(gbase);
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(smem_raw + S::TW_BYTES + 64);     // in group 0's control block
     cplx* buf = reinterpret_cast<cplx*>(gbase + S::CTRL_BYTES);
     Torus* acc = reinterpret_cast<Torus*>(gbase + S::CTRL_BYTES + S::BUF_BYTES);
-    unsigned char* kb1 = gbase + S::CTRL_BYTES + S::BUF_BYTES + S::ACC_BYTES;
-    uint32_t* pk = reinterpret_cast<uint32_t*>(kb1 + S::KB1_BYTES);
 
     for (int i = threadIdx.x; i < P::TW_TOTAL; i += GROUPS * T) tw[i] = A.tw[i];
-    if (t == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    if (t == 0) { mbar_init(&bars[0], 1); mbar_fence_init(); }
+    if (warp == 0) {     // the whole SM's tensor memory: one CTA per SM (shared-memory bound), nobody else wants it
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_base_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_slot;
+    const uint32_t tacc = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 128u;
     BkSlot s0{&bars[0], reinterpret_cast<unsigned char*>(buf), 0u};
-    BkSlot s1{&bars[1], kb1, 0u};
 
     // unit = (sample, test-vector index); n_mu > 1 only on the circuit-bootstrap path
     const int n_mu = A.n_mu > 0 ? A.n_mu : 1;
     const long unit = (long)blockIdx.x * GROUPS + g;
-    if (unit >= (long)A.count * n_mu) return;          // whole group leaves; nothing is shared between groups
-    const int ct = (int)(unit / n_mu), w = (int)(unit % n_mu);
-    const int n = A.n;
-    const int l = LT == 2 ? 2 : A.l;
+    if (unit < (long)A.count * n_mu) {                 // idle groups of the last CTA fall through to the final barrier
+        const int ct = (int)(unit / n_mu), w = (int)(unit % n_mu);
+        const int n = A.n;
+        const int l = A.l;
 
-    // ---- the initial accumulator
-    Torus mu = (Torus)A.mu;
-    if (sizeof(Torus) == 8 && A.mode == BR_LWE && A.mu_bgbit > 0) mu = (Torus)(1ull << (64 - (w + 1) * A.mu_bgbit));   // mu_w, poc:846
-    if (A.mode == BR_ACCUM) {
-        const Torus* src = reinterpret_cast<const Torus*>(A.accum) + (size_t)ct * 2 * N;
-        for (int j = t; j < 2 * N; j += T) acc[j] = src[j];
-    } else {
-        // testvectbis = X^(2N - barb) * v  (cb/lwe_functions.cpp:385; defect D3 of the PoC corrected the same way)
-        const int barb = fetch_bara<LOGM, Torus>(A, ct, n);
-        const int rot = (2 * N - barb) & (2 * N - 1);
-        const Torus* v = reinterpret_cast<const Torus*>(A.v);
-        for (int j = t; j < N; j += T) {
-            const int idx = (j - rot) & (2 * N - 1);
-            const int k0 = idx & (N - 1);
-            Torus val;
-            if (A.mode == BR_TESTVEC) val = v[k0];
-            else if (sizeof(Torus) == 4) val = mu;                              // [mu,...,mu]  :422
-            else val = (k0 < M) ? (Torus)(0 - (U)(mu / 2)) : (Torus)(mu / 2);   // -mu/2 | +mu/2  poc:552-553
-            acc[j] = 0;                                                          // tLweNoiselessTrivial
-            acc[N + j] = (idx & N) ? (Torus)(0 - (U)val) : val;
+        // ---- the initial accumulator
+        Torus mu = (Torus)A.mu;
+        if (sizeof(Torus) == 8 && A.mode == BR_LWE && A.mu_bgbit > 0) mu = (Torus)(1ull << (64 - (w + 1) * A.mu_bgbit));   // mu_w, poc:846
+        if (A.mode == BR_ACCUM) {
+            const Torus* src = reinterpret_cast<const Torus*>(A.accum) + (size_t)ct * 2 * N;
+            for (int j = t; j < 2 * N; j += T) acc[j] = src[j];
+        } else {
+            // testvectbis = X^(2N - barb) * v  (cb/lwe_functions.cpp:385; defect D3 of the PoC corrected the same way)
+            const int barb = fetch_bara<LOGM, Torus>(A, ct, n);
+            const int rot = (2 * N - barb) & (2 * N - 1);
+            const Torus* v = reinterpret_cast<const Torus*>(A.v);
+            for (int j = t; j < N; j += T) {
+                const int idx = (j - rot) & (2 * N - 1);
+                const int k0 = idx & (N - 1);
+                Torus val;
+                if (A.mode == BR_TESTVEC) val = v[k0];
+                else if (sizeof(Torus) == 4) val = mu;                              // [mu,...,mu]  :422
+                else val = (k0 < M) ? (Torus)(0 - (U)(mu / 2)) : (Torus)(mu / 2);   // -mu/2 | +mu/2  poc:552-553
+                acc[j] = 0;                                                          // tLweNoiselessTrivial
+                acc[N + j] = (idx & N) ? (Torus)(0 - (U)val) : val;
+            }
+        }
+        lanes_sync<T>(bar_id);
+
+        // ---- n CMUX steps (tfhe_blindRotate_FFT :348-354); a step with bara == 0 is skipped like the reference does (:350).
+        // The next rotation amount is fetched one step ahead.
+        const size_t bk_stride = (size_t)2 * l * 2 * M;
+        int a_next = fetch_bara<LOGM, Torus>(A, ct, 0);
+        for (int i = 0; i < n; i++) {
+            const int a = a_next;
+            if (i + 1 < n) a_next = fetch_bara<LOGM, Torus>(A, ct, i + 1);
+            if (a == 0) continue;
+            cmux_step<LOGM, Torus>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, s0, tw, t, bar_id);
+        }
+
+        // ---- epilogue
+        if (A.mode == BR_ACCUM) {
+            Torus* dst = reinterpret_cast<Torus*>(A.accum) + (size_t)ct * 2 * N;
+            for (int j = t; j < 2 * N; j += T) dst[j] = acc[j];
+        } else {
+            // tLweExtractLweSampleIndex(index 0) cb/tlwe_functions.cpp:351-363 ; PoC adds mu/2 to b (:648)
+            Torus* out = reinterpret_cast<Torus*>(A.out) + (size_t)unit * A.out_stride;
+            for (int j = t; j < N; j += T) out[j] = (j == 0) ? acc[0] : (Torus)(0 - (U)acc[N - j]);
+            if (t == 0) {
+                U b = (U)acc[N];
+                if (sizeof(Torus) == 8 && A.mode == BR_LWE) b += (U)(mu / 2);
+                out[N] = (Torus)b;
+            }
         }
     }
-    lanes_sync<T>(bar_id);
-
-    // ---- n CMUX steps (tfhe_blindRotate_FFT :348-354); a step with bara == 0 is skipped like the reference does (:350).
-    // The next rotation amount is fetched one step ahead.
-    const size_t bk_stride = (size_t)2 * l * 2 * M;
-    int a_next = fetch_bara<LOGM, Torus>(A, ct, 0);
-    for (int i = 0; i < n; i++) {
-        const int a = a_next;
-        if (i + 1 < n) a_next = fetch_bara<LOGM, Torus>(A, ct, i + 1);
-        if (a == 0) continue;
-        cmux_step<LOGM, Torus, LT>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, pk, s0, s1, tw, t, bar_id);
-    }
-
-    // ---- epilogue
-    if (A.mode == BR_ACCUM) {
-        Torus* dst = reinterpret_cast<Torus*>(A.accum) + (size_t)ct * 2 * N;
-        for (int j = t; j < 2 * N; j += T) dst[j] = acc[j];
-    } else {
-        // tLweExtractLweSampleIndex(index 0) cb/tlwe_functions.cpp:351-363 ; PoC adds mu/2 to b (:648)
-        Torus* out = reinterpret_cast<Torus*>(A.out) + (size_t)unit * A.out_stride;
-        for (int j = t; j < N; j += T) out[j] = (j == 0) ? acc[0] : (Torus)(0 - (U)acc[N - j]);
-        if (t == 0) {
-            U b = (U)acc[N];
-            if (sizeof(Torus) == 8 && A.mode == BR_LWE) b += (U)(mu / 2);
-            out[N] = (Torus)b;
-        }
-    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 static bool g_inited = false;
-constexpr int G32 = 8, G64 = 3;     // accumulators per CTA: 8 warps (N=1024) / 3 x 2 warps (N=2048)
+constexpr int G32 = 12, G64 = 4;     // accumulators per CTA: 12 warps (N=1024) / 4 x 2 warps (N=2048)
 
-template <int LOGM, typename Torus, int GROUPS, int LT> static cudaError_t br_attr() {
-    return cudaFuncSetAttribute(blind_rotate_kernel<LOGM, Torus, GROUPS, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)BRSmem<LOGM, Torus, GROUPS, LT>::TOTAL);
+template <int LOGM, typename Torus, int GROUPS> static cudaError_t br_attr() {
+    return cudaFuncSetAttribute(blind_rotate_kernel<LOGM, Torus, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)BRSmem<LOGM, Torus, GROUPS>::TOTAL);
 }
 cudaError_t blind_rotate_init() {
     cudaError_t e;
-    if ((e = br_attr<9, int32_t, G32, 2>()) != cudaSuccess) return e;
-    if ((e = br_attr<9, int32_t, G32, 0>()) != cudaSuccess) return e;
-    if ((e = br_attr<10, int64_t, G64, 0>()) != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, G32>()) != cudaSuccess) return e;
+    if ((e = br_attr<10, int64_t, G64>()) != cudaSuccess) return e;
     g_inited = true;
     return cudaSuccess;
 }
@@ -304,13 +325,7 @@ cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
     if (!g_inited) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
     if (a.count <= 0) return cudaSuccess;
     const int grid = (a.count + G32 - 1) / G32;
-    // The packed two-digit path (LT = 2) saves one accumulator re-read per CMUX but currently costs 80 B of spills;
-    // measured 145k vs 158k bootstraps/s (profiles/r1_notes.md), so the re-read path is the default.
-    static const bool use_packed = getenv("TFHE_B200_PACKED_DIGITS") != nullptr;   // development knob
-    if (a.l == 2 && use_packed)
-        blind_rotate_kernel<9, int32_t, G32, 2><<<grid, G32 * TreePlan<9>::T, BRSmem<9, int32_t, G32, 2>::TOTAL, s>>>(a);
-    else
-        blind_rotate_kernel<9, int32_t, G32, 0><<<grid, G32 * TreePlan<9>::T, BRSmem<9, int32_t, G32, 0>::TOTAL, s>>>(a);
+    blind_rotate_kernel<9, int32_t, G32><<<grid, G32 * TreePlan<9>::T, BRSmem<9, int32_t, G32>::TOTAL, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
@@ -318,7 +333,7 @@ cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
     if (a.count <= 0) return cudaSuccess;
     const long units = (long)a.count * (a.n_mu > 0 ? a.n_mu : 1);
     const int grid = (int)((units + G64 - 1) / G64);
-    blind_rotate_kernel<10, int64_t, G64, 0><<<grid, G64 * TreePlan<10>::T, BRSmem<10, int64_t, G64, 0>::TOTAL, s>>>(a);
+    blind_rotate_kernel<10, int64_t, G64><<<grid, G64 * TreePlan<10>::T, BRSmem<10, int64_t, G64>::TOTAL, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -12,6 +12,7 @@
 // Device key layout: int32 [rows][t][base-1][cols_pad]  (d = 0 rows are never read by the reference either).
 #include "engine.h"
 #include <type_traits>
+#include <cstdlib>
 
 namespace tfhe_b200 {
 
@@ -19,8 +20,8 @@ constexpr int KS_TILE = 32;     // samples per CTA
 constexpr int KS_HALF = 16;     // samples per thread
 constexpr int KS_ICHUNK = 32;   // input coefficients staged per shared-memory refill
 
-template <typename TorusIn, int BASEBIT>
-__global__ void __launch_bounds__(256) keyswitch_kernel(const KSArgs A) {
+template <typename TorusIn, int BASEBIT, int VARIANT>
+__global__ void __launch_bounds__(256, 2) keyswitch_kernel(const KSArgs A) {
     typedef typename std::conditional<sizeof(TorusIn) == 4, uint32_t, uint64_t>::type U;
     constexpr int W = sizeof(TorusIn) * 8;
     constexpr int BASE = 1 << BASEBIT;
@@ -57,18 +58,32 @@ __global__ void __launch_bounds__(256) keyswitch_kernel(const KSArgs A) {
             for (int s = 0; s < KS_HALF; s++) a[s] = abar[half * KS_HALF + s][ii];
             const int4* krow = key4 + ((size_t)(i0 + ii) * A.t) * (BASE - 1) * (row_stride / 4);
             for (int j = 0; j < A.t; j++) {
-                int4 r[BASE - 1];
-#pragma unroll
-                for (int d = 0; d < BASE - 1; d++) r[d] = __ldg(krow + ((size_t)j * (BASE - 1) + d) * (row_stride / 4));
                 const int sh = W - (j + 1) * BASEBIT;
+                if (VARIANT == 0) {
+                    // candidate rows in registers, every sample picks one (predicated subtracts)
+                    int4 r[BASE - 1];
 #pragma unroll
-                for (int s = 0; s < KS_HALF; s++) {
-                    const int dg = (int)((a[s] >> sh) & (U)(BASE - 1));
+                    for (int d = 0; d < BASE - 1; d++) r[d] = __ldg(krow + ((size_t)j * (BASE - 1) + d) * (row_stride / 4));
 #pragma unroll
-                    for (int d = 0; d < BASE - 1; d++) {
-                        if (dg == d + 1) {
-                            acc[s].x -= r[d].x; acc[s].y -= r[d].y; acc[s].z -= r[d].z; acc[s].w -= r[d].w;
+                    for (int s = 0; s < KS_HALF; s++) {
+                        const int dg = (int)((a[s] >> sh) & (U)(BASE - 1));
+#pragma unroll
+                        for (int d = 0; d < BASE - 1; d++) {
+                            if (dg == d + 1) {
+                                acc[s].x -= r[d].x; acc[s].y -= r[d].y; acc[s].z -= r[d].z; acc[s].w -= r[d].w;
+                            }
                         }
+                    }
+                } else {
+                    // every sample loads the row its digit selects (the base-1 rows of (i,j) stay hot in L1); digit 0 reads
+                    // row 0 and is masked out, so there is no branch and no select
+                    const int4* kj = krow + (size_t)j * (BASE - 1) * (row_stride / 4);
+#pragma unroll
+                    for (int s = 0; s < KS_HALF; s++) {
+                        const int dg = (int)((a[s] >> sh) & (U)(BASE - 1));
+                        const int keep = dg != 0 ? -1 : 0;
+                        const int4 r = __ldg(kj + (size_t)max(dg - 1, 0) * (row_stride / 4));
+                        acc[s].x -= r.x & keep; acc[s].y -= r.y & keep; acc[s].z -= r.z & keep; acc[s].w -= r.w & keep;
                     }
                 }
             }
@@ -97,11 +112,21 @@ static cudaError_t launch_ks(const KSArgs& a, cudaStream_t s) {
     if (a.count <= 0) return cudaSuccess;
     if (a.cols_pad % 512) return cudaErrorInvalidValue;
     dim3 grid((a.count + KS_TILE - 1) / KS_TILE, a.cols_pad / 512);
-    switch (a.basebit) {
-        case 1: keyswitch_kernel<TorusIn, 1><<<grid, 256, 0, s>>>(a); break;
-        case 2: keyswitch_kernel<TorusIn, 2><<<grid, 256, 0, s>>>(a); break;
-        case 3: keyswitch_kernel<TorusIn, 3><<<grid, 256, 0, s>>>(a); break;
-        default: return cudaErrorInvalidValue;
+    static const int variant = getenv("TFHE_B200_KS_VARIANT") ? atoi(getenv("TFHE_B200_KS_VARIANT")) : 0;   // development knob
+    if (variant == 0) {
+        switch (a.basebit) {
+            case 1: keyswitch_kernel<TorusIn, 1, 0><<<grid, 256, 0, s>>>(a); break;
+            case 2: keyswitch_kernel<TorusIn, 2, 0><<<grid, 256, 0, s>>>(a); break;
+            case 3: keyswitch_kernel<TorusIn, 3, 0><<<grid, 256, 0, s>>>(a); break;
+            default: return cudaErrorInvalidValue;
+        }
+    } else {
+        switch (a.basebit) {
+            case 1: keyswitch_kernel<TorusIn, 1, 1><<<grid, 256, 0, s>>>(a); break;
+            case 2: keyswitch_kernel<TorusIn, 2, 1><<<grid, 256, 0, s>>>(a); break;
+            case 3: keyswitch_kernel<TorusIn, 3, 1><<<grid, 256, 0, s>>>(a); break;
+            default: return cudaErrorInvalidValue;
+        }
     }
     return cudaGetLastError();
 }
