@@ -68,6 +68,10 @@ __device__ __forceinline__ int modswitch32(int32_t x, int log2Msize) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"       \
                  ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), \
                    "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(addr) : "memory")
+#define TFHE_TLD4(r, addr) \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory")
+#define TFHE_TST4(r, addr) \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(addr) : "memory")
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -106,26 +110,43 @@ __device__ __forceinline__ void load_tmem(cplx (&R)[16], const uint32_t taddr) {
 // forward transform of one digit polynomial + its two multiply-accumulates.  Key polynomial BK[p][0] lands in the transpose
 // buffer by TMA as soon as the transpose is over (bk_pipe.cuh); BK[p][1] is prefetched into registers (the accumulators no
 // longer occupy them) while the second half of the transform runs.
-template <int LOGM, bool FIRST>
+template <int LOGM, bool FIRST, bool ALLREG>
 __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t tacc, const cplx* __restrict__ bkp,
                                                 cplx* __restrict__ buf, BkSlot& s0,
                                                 const cplx* __restrict__ tw, const int t, const int bar_id) {
     typedef TreePlan<LOGM> P;
     constexpr uint32_t POLY = P::M * sizeof(cplx);
     tree_forward_a<LOGM>(v, buf, tw, t, bar_id);                // ends with a sync: nobody reads buf any more
-    if (t == 0) s0.request(bkp, POLY);
+    if (!ALLREG && t == 0) s0.request(bkp, POLY);
+    tree_forward_b<LOGM>(v, tw, t);
+    // BK[p][1] goes to registers: requested after depths 4-7 (v + 16 key values + that pass's temporaries do not fit in 168
+    // registers), its L2 round trip hides behind the shuffle stage and the first multiply-accumulate
+    const cplx* __restrict__ g1 = bkp + P::M + t;
+    asm volatile("" : "+l"(g1) : "d"(v[0].x), "d"(v[15].y));          // do not hoist the loads above the pass
     cplx b1[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) b1[i] = __ldg(bkp + P::M + i * P::T + t);
-    tree_forward_b<LOGM>(v, tw, t);
-    s0.wait();
-    const cplx* b0 = reinterpret_cast<const cplx*>(s0.dst) + t;
-    mac_tmem<FIRST>(tacc, v, [&](int i) { return b0[i * P::T]; });
-    mac_tmem<FIRST>(tacc + 64, v, [&](int i) { return b1[i]; });
+    for (int i = 0; i < 16; i++) b1[i] = __ldg(g1 + i * P::T);
+    if (ALLREG) {
+        // 8-warp configuration: enough registers to take BK[p][0] the same way (no shared-memory traffic for the key at all)
+        cplx b0r[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) b0r[i] = __ldg(g1 - P::M + i * P::T);
+        tree_forward_c<LOGM>(v, tw, t);
+        mac_tmem<FIRST>(tacc, v, [&](int i) { return b0r[i]; });
+        mac_tmem<FIRST>(tacc + 64, v, [&](int i) { return b1[i]; });
+    } else {
+        tree_forward_c<LOGM>(v, tw, t);
+        s0.wait();
+        const cplx* b0 = reinterpret_cast<const cplx*>(s0.dst) + t;
+        mac_tmem<FIRST>(tacc, v, [&](int i) { return b0[i * P::T]; });
+        mac_tmem<FIRST>(tacc + 64, v, [&](int i) { return b1[i]; });
+    }
 }
 
 // One CMUX: ACC <- ACC + BK_i (x) ((X^a - 1) ACC).   acc: shared [2][N].  bk: BK_i = [2l][2][M] spectra (scaled 2/N).
-template <int LOGM, typename Torus>
+// PACK2 (l == 2): both gadget digits of a coefficient come from ONE rotated read of the accumulator; the second-level digits
+// wait, packed two per word, in 16 TMEM columns of this lane.  Otherwise the accumulator is re-read per level.
+template <int LOGM, typename Torus, bool PACK2, bool ALLREG>
 __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, const cplx* __restrict__ bk,
                                           const int l, const int Bgbit, cplx* __restrict__ buf, const uint32_t tacc,
                                           BkSlot& s0, const cplx* __restrict__ tw, const int t, const int bar_id) {
@@ -142,18 +163,40 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
         const Torus* __restrict__ aq = acc + q * N;
         const int sh = W - (lev + 1) * Bgbit;
         cplx v[16];
-        int a2 = a;
-        asm volatile("" : "+r"(a2));          // keep the 32 rotated addresses from being hoisted out of the loop
+        if (PACK2 && lev == 1) {
 #pragma unroll
-        for (int m = 0; m < 16; m++) {
-            const int j = t + T * m;
-            const U ure = (U)rot_minus_one<Torus, N>(aq, j, a2) + offset;
-            const U uim = (U)rot_minus_one<Torus, N>(aq, j + M, a2) + offset;
-            v[m] = make_double2((double)((int)((uint32_t)(ure >> sh) & mask) - half),
-                                (double)((int)((uint32_t)(uim >> sh) & mask) - half));
+            for (int c = 0; c < 4; c++) {
+                uint32_t pk[4];
+                TFHE_TLD4(pk, tacc + 128 + 4 * c);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[4 * c + i] = make_double2((double)((int)(pk[i] << 16) >> 16), (double)((int)pk[i] >> 16));
+            }
+        } else {
+            int a2 = a;
+            asm volatile("" : "+r"(a2));          // keep the 32 rotated addresses from being hoisted out of the loop
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int j = t + T * (4 * c + i);
+                    const U ure = (U)rot_minus_one<Torus, N>(aq, j, a2) + offset;
+                    const U uim = (U)rot_minus_one<Torus, N>(aq, j + M, a2) + offset;
+                    v[4 * c + i] = make_double2((double)((int)((uint32_t)(ure >> sh) & mask) - half),
+                                                (double)((int)((uint32_t)(uim >> sh) & mask) - half));
+                    if (PACK2) {
+                        const uint32_t d1r = (uint32_t)((int)((uint32_t)(ure >> (sh - Bgbit)) & mask) - half);
+                        const uint32_t d1i = (uint32_t)((int)((uint32_t)(uim >> (sh - Bgbit)) & mask) - half);
+                        pk[i] = (d1r & 0xFFFFu) | (d1i << 16);
+                    }
+                }
+                if (PACK2) TFHE_TST4(pk, tacc + 128 + 4 * c);
+            }
+            if (PACK2) tmem_wait_st();
         }
-        if (p == 0) forward_and_mac<LOGM, true>(v, tacc, bk, buf, s0, tw, t, bar_id);
-        else        forward_and_mac<LOGM, false>(v, tacc, bk + (size_t)(p * 2) * M, buf, s0, tw, t, bar_id);
+        if (p == 0) forward_and_mac<LOGM, true, ALLREG>(v, tacc, bk, buf, s0, tw, t, bar_id);
+        else        forward_and_mac<LOGM, false, ALLREG>(v, tacc, bk + (size_t)(p * 2) * M, buf, s0, tw, t, bar_id);
     }
     // every lane has finished reading the accumulator once it passes the first sync inside tree_backward
     {
@@ -192,7 +235,7 @@ template <int LOGM, typename Torus, int GROUPS> struct BRSmem {
     static constexpr int WARPS = GROUPS * P::T / 32;
     static_assert(sizeof(cplx) * P::BUF >= sizeof(cplx) * P::M, "transpose buffer must hold one key polynomial");
     static_assert(TOTAL <= 232448, "shared memory budget (227 KB) exceeded");
-    static_assert((WARPS + 3) / 4 * 128 <= 512, "tensor memory: 128 columns per warp, 4 lane quarters");
+    static_assert((WARPS + 3) / 4 * 144 <= 512, "tensor memory: 144 columns per warp, 4 lane quarters");
 };
 
 // rotation amount i of sample ct (i == n: the b part), straight from the kernel's inputs -- nothing is staged in shared memory
@@ -214,7 +257,7 @@ __device__ __forceinline__ int fetch_bara(const BRArgs& A, const int ct, const i
     return __ldg(A.bara + (size_t)ct * n + i);
 }
 
-template <int LOGM, typename Torus, int GROUPS>
+template <int LOGM, typename Torus, int GROUPS, bool PACK2, bool ALLREG>
 __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_kernel(const BRArgs A) {
     typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
@@ -240,7 +283,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_base_slot;
-    const uint32_t tacc = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 128u;
+    const uint32_t tacc = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 144u;   // R0 | R1 | packed digits
     BkSlot s0{&bars[0], reinterpret_cast<unsigned char*>(buf), 0u};
 
     // unit = (sample, test-vector index); n_mu > 1 only on the circuit-bootstrap path
@@ -249,7 +292,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
     if (unit < (long)A.count * n_mu) {                 // idle groups of the last CTA fall through to the final barrier
         const int ct = (int)(unit / n_mu), w = (int)(unit % n_mu);
         const int n = A.n;
-        const int l = A.l;
+        const int l = PACK2 ? 2 : A.l;
 
         // ---- the initial accumulator
         Torus mu = (Torus)A.mu;
@@ -283,7 +326,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
             const int a = a_next;
             if (i + 1 < n) a_next = fetch_bara<LOGM, Torus>(A, ct, i + 1);
             if (a == 0) continue;
-            cmux_step<LOGM, Torus>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, s0, tw, t, bar_id);
+            cmux_step<LOGM, Torus, PACK2, ALLREG>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, s0, tw, t, bar_id);
         }
 
         // ---- epilogue
@@ -307,16 +350,20 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
 }
 
 static bool g_inited = false;
-constexpr int G32 = 12, G64 = 4;     // accumulators per CTA: 12 warps (N=1024) / 4 x 2 warps (N=2048)
+// Configurations (profiles/r1_notes.md has the sweep): 8 warps per SM with every key value prefetched into registers is the
+// fastest (166 k bootstraps/s); 12 warps with BK[p][0] landing in shared memory by TMA is kept for comparison (146 k/s).
+constexpr int G32 = 8, G32_TMA = 12, G64 = 4;     // accumulators per CTA (N=1024: one warp each; N=2048: two warps each)
 
-template <int LOGM, typename Torus, int GROUPS> static cudaError_t br_attr() {
-    return cudaFuncSetAttribute(blind_rotate_kernel<LOGM, Torus, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int LOGM, typename Torus, int GROUPS, bool PACK2, bool ALLREG> static cudaError_t br_attr() {
+    return cudaFuncSetAttribute(blind_rotate_kernel<LOGM, Torus, GROUPS, PACK2, ALLREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)BRSmem<LOGM, Torus, GROUPS>::TOTAL);
 }
 cudaError_t blind_rotate_init() {
     cudaError_t e;
-    if ((e = br_attr<9, int32_t, G32>()) != cudaSuccess) return e;
-    if ((e = br_attr<10, int64_t, G64>()) != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, G32, false, true>()) != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, G32_TMA, false, false>()) != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, G32_TMA, true, false>()) != cudaSuccess) return e;
+    if ((e = br_attr<10, int64_t, G64, false, true>()) != cudaSuccess) return e;
     g_inited = true;
     return cudaSuccess;
 }
@@ -324,8 +371,18 @@ cudaError_t blind_rotate_init() {
 cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
     if (!g_inited) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
     if (a.count <= 0) return cudaSuccess;
-    const int grid = (a.count + G32 - 1) / G32;
-    blind_rotate_kernel<9, int32_t, G32><<<grid, G32 * TreePlan<9>::T, BRSmem<9, int32_t, G32>::TOTAL, s>>>(a);
+    // development knob: TFHE_B200_BR_VARIANT = tma | tma_pack selects the measured alternatives
+    static const char* variant = getenv("TFHE_B200_BR_VARIANT");
+    if (variant && variant[0] == 't') {
+        const int grid = (a.count + G32_TMA - 1) / G32_TMA;
+        if (a.l == 2 && variant[3] == '_')
+            blind_rotate_kernel<9, int32_t, G32_TMA, true, false><<<grid, G32_TMA * TreePlan<9>::T, BRSmem<9, int32_t, G32_TMA>::TOTAL, s>>>(a);
+        else
+            blind_rotate_kernel<9, int32_t, G32_TMA, false, false><<<grid, G32_TMA * TreePlan<9>::T, BRSmem<9, int32_t, G32_TMA>::TOTAL, s>>>(a);
+    } else {
+        const int grid = (a.count + G32 - 1) / G32;
+        blind_rotate_kernel<9, int32_t, G32, false, true><<<grid, G32 * TreePlan<9>::T, BRSmem<9, int32_t, G32>::TOTAL, s>>>(a);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
@@ -333,7 +390,7 @@ cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
     if (a.count <= 0) return cudaSuccess;
     const long units = (long)a.count * (a.n_mu > 0 ? a.n_mu : 1);
     const int grid = (int)((units + G64 - 1) / G64);
-    blind_rotate_kernel<10, int64_t, G64><<<grid, G64 * TreePlan<10>::T, BRSmem<10, int64_t, G64>::TOTAL, s>>>(a);
+    blind_rotate_kernel<10, int64_t, G64, false, true><<<grid, G64 * TreePlan<10>::T, BRSmem<10, int64_t, G64>::TOTAL, s>>>(a);
     return cudaGetLastError();
 }
 

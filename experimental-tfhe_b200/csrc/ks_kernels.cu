@@ -4,7 +4,7 @@
 // (cb/poc_CircuitBootstrapping.cpp:437-465) and circuitPrivKS (:667-698):
 //     result = (0,b) - sum_{i<rows, j<t} key[i][j][ d_ij ],   d_ij = ((a_i + prec_offset) >> (W-(j+1)basebit)) & (base-1), d_ij != 0
 // The reference walks the table once per sample (12.3 MB of rows per gate, 147 MB per private key switch).
-// Here a CTA owns a tile of KS_TILE samples x 512 output columns: for every (i,j) it fetches the base-1
+// Here a CTA owns a tile of KS_TILE (32) samples x 512 output columns: for every (i,j) it fetches the base-1
 // candidate rows ONCE (coalesced 16-byte loads) and each sample of the tile subtracts the row its digit
 // selects, so table traffic per sample drops by ~KS_TILE*(base-1)/base / (base-1).  Digits are uniform across
 // a warp (all lanes of a warp work on the same samples), so the selection is a uniform branch.
@@ -17,28 +17,31 @@
 namespace tfhe_b200 {
 
 constexpr int KS_TILE = 32;     // samples per CTA
-constexpr int KS_HALF = 16;     // samples per thread
+constexpr int KS_S = 8;         // samples per thread
 constexpr int KS_ICHUNK = 32;   // input coefficients staged per shared-memory refill
 
-template <typename TorusIn, int BASEBIT, int VARIANT>
+// Thread layout: 64 column groups (8 consecutive int32 columns = two int4 each) x 4 sample groups (8 samples each).
+// A warp is 32 column groups of ONE sample group, so a sample's digit is warp-uniform and picking the row is a uniform branch.
+// 8 columns per thread (instead of 4) halves the per-add overhead of digit extraction and branching (profiles/r1_notes.md).
+template <typename TorusIn, int BASEBIT>
 __global__ void __launch_bounds__(256, 2) keyswitch_kernel(const KSArgs A) {
     typedef typename std::conditional<sizeof(TorusIn) == 4, uint32_t, uint64_t>::type U;
     constexpr int W = sizeof(TorusIn) * 8;
     constexpr int BASE = 1 << BASEBIT;
     __shared__ U abar[KS_TILE][KS_ICHUNK + 1];
 
-    const int cg = threadIdx.x & 127;           // column group: 4 consecutive int32 columns
-    const int half = threadIdx.x >> 7;          // which 16 samples of the tile
+    const int cg = threadIdx.x & 63;            // column group: columns [8 cg, 8 cg + 8) of this CTA's 512-column slice
+    const int sg = threadIdx.x >> 6;            // sample group
     const int s0 = blockIdx.x * KS_TILE;        // first sample of the tile
-    const int col0 = blockIdx.y * 512 + cg * 4;
+    const int col0 = blockIdx.y * 512 + cg * 8;
     const TorusIn* in = reinterpret_cast<const TorusIn*>(A.in);
     const U prec_offset = (U)1 << (W - (1 + BASEBIT * A.t));      // cb/lwe_functions.cpp:141 ; poc:444,674
 
-    int4 acc[KS_HALF];
+    int4 acc0[KS_S], acc1[KS_S];
 #pragma unroll
-    for (int s = 0; s < KS_HALF; s++) acc[s] = make_int4(0, 0, 0, 0);
+    for (int s = 0; s < KS_S; s++) { acc0[s] = make_int4(0, 0, 0, 0); acc1[s] = make_int4(0, 0, 0, 0); }
 
-    const size_t row_stride = (size_t)A.cols_pad;                 // one key row
+    const size_t rs4 = (size_t)A.cols_pad / 4;                    // one key row, in int4
     const int4* key4 = reinterpret_cast<const int4*>(A.key + col0);
 
     for (int i0 = 0; i0 < A.rows_in; i0 += KS_ICHUNK) {
@@ -53,37 +56,27 @@ __global__ void __launch_bounds__(256, 2) keyswitch_kernel(const KSArgs A) {
         __syncthreads();
         const int iend = min(KS_ICHUNK, A.rows_in - i0);
         for (int ii = 0; ii < iend; ii++) {
-            U a[KS_HALF];
+            U a[KS_S];
 #pragma unroll
-            for (int s = 0; s < KS_HALF; s++) a[s] = abar[half * KS_HALF + s][ii];
-            const int4* krow = key4 + ((size_t)(i0 + ii) * A.t) * (BASE - 1) * (row_stride / 4);
+            for (int s = 0; s < KS_S; s++) a[s] = abar[sg * KS_S + s][ii];
+            const int4* krow = key4 + ((size_t)(i0 + ii) * A.t) * (BASE - 1) * rs4;
             for (int j = 0; j < A.t; j++) {
                 const int sh = W - (j + 1) * BASEBIT;
-                if (VARIANT == 0) {
-                    // candidate rows in registers, every sample picks one (predicated subtracts)
-                    int4 r[BASE - 1];
+                int4 r0[BASE - 1], r1[BASE - 1];
 #pragma unroll
-                    for (int d = 0; d < BASE - 1; d++) r[d] = __ldg(krow + ((size_t)j * (BASE - 1) + d) * (row_stride / 4));
+                for (int d = 0; d < BASE - 1; d++) {
+                    const int4* rp = krow + ((size_t)j * (BASE - 1) + d) * rs4;
+                    r0[d] = __ldg(rp); r1[d] = __ldg(rp + 1);
+                }
 #pragma unroll
-                    for (int s = 0; s < KS_HALF; s++) {
-                        const int dg = (int)((a[s] >> sh) & (U)(BASE - 1));
+                for (int s = 0; s < KS_S; s++) {
+                    const int dg = (int)((a[s] >> sh) & (U)(BASE - 1));
 #pragma unroll
-                        for (int d = 0; d < BASE - 1; d++) {
-                            if (dg == d + 1) {
-                                acc[s].x -= r[d].x; acc[s].y -= r[d].y; acc[s].z -= r[d].z; acc[s].w -= r[d].w;
-                            }
+                    for (int d = 0; d < BASE - 1; d++) {
+                        if (dg == d + 1) {
+                            acc0[s].x -= r0[d].x; acc0[s].y -= r0[d].y; acc0[s].z -= r0[d].z; acc0[s].w -= r0[d].w;
+                            acc1[s].x -= r1[d].x; acc1[s].y -= r1[d].y; acc1[s].z -= r1[d].z; acc1[s].w -= r1[d].w;
                         }
-                    }
-                } else {
-                    // every sample loads the row its digit selects (the base-1 rows of (i,j) stay hot in L1); digit 0 reads
-                    // row 0 and is masked out, so there is no branch and no select
-                    const int4* kj = krow + (size_t)j * (BASE - 1) * (row_stride / 4);
-#pragma unroll
-                    for (int s = 0; s < KS_HALF; s++) {
-                        const int dg = (int)((a[s] >> sh) & (U)(BASE - 1));
-                        const int keep = dg != 0 ? -1 : 0;
-                        const int4 r = __ldg(kj + (size_t)max(dg - 1, 0) * (row_stride / 4));
-                        acc[s].x -= r.x & keep; acc[s].y -= r.y & keep; acc[s].z -= r.z & keep; acc[s].w -= r.w & keep;
                     }
                 }
             }
@@ -91,12 +84,12 @@ __global__ void __launch_bounds__(256, 2) keyswitch_kernel(const KSArgs A) {
     }
     // result starts as the noiseless trivial sample (0,b) (cb/lwe_functions.cpp:169) or 0 (poc:677-681)
 #pragma unroll
-    for (int s = 0; s < KS_HALF; s++) {
-        const int smp = s0 + half * KS_HALF + s;
+    for (int s = 0; s < KS_S; s++) {
+        const int smp = s0 + sg * KS_S + s;
         if (smp >= A.count) continue;
-        int v[4] = {acc[s].x, acc[s].y, acc[s].z, acc[s].w};
+        const int v[8] = {acc0[s].x, acc0[s].y, acc0[s].z, acc0[s].w, acc1[s].x, acc1[s].y, acc1[s].z, acc1[s].w};
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
+        for (int c = 0; c < 8; c++) {
             const int col = col0 + c;
             if (col < A.cols) {
                 int32_t x = v[c];
@@ -112,21 +105,11 @@ static cudaError_t launch_ks(const KSArgs& a, cudaStream_t s) {
     if (a.count <= 0) return cudaSuccess;
     if (a.cols_pad % 512) return cudaErrorInvalidValue;
     dim3 grid((a.count + KS_TILE - 1) / KS_TILE, a.cols_pad / 512);
-    static const int variant = getenv("TFHE_B200_KS_VARIANT") ? atoi(getenv("TFHE_B200_KS_VARIANT")) : 0;   // development knob
-    if (variant == 0) {
-        switch (a.basebit) {
-            case 1: keyswitch_kernel<TorusIn, 1, 0><<<grid, 256, 0, s>>>(a); break;
-            case 2: keyswitch_kernel<TorusIn, 2, 0><<<grid, 256, 0, s>>>(a); break;
-            case 3: keyswitch_kernel<TorusIn, 3, 0><<<grid, 256, 0, s>>>(a); break;
-            default: return cudaErrorInvalidValue;
-        }
-    } else {
-        switch (a.basebit) {
-            case 1: keyswitch_kernel<TorusIn, 1, 1><<<grid, 256, 0, s>>>(a); break;
-            case 2: keyswitch_kernel<TorusIn, 2, 1><<<grid, 256, 0, s>>>(a); break;
-            case 3: keyswitch_kernel<TorusIn, 3, 1><<<grid, 256, 0, s>>>(a); break;
-            default: return cudaErrorInvalidValue;
-        }
+    switch (a.basebit) {
+        case 1: keyswitch_kernel<TorusIn, 1><<<grid, 256, 0, s>>>(a); break;
+        case 2: keyswitch_kernel<TorusIn, 2><<<grid, 256, 0, s>>>(a); break;
+        case 3: keyswitch_kernel<TorusIn, 3><<<grid, 256, 0, s>>>(a); break;
+        default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }

@@ -88,6 +88,19 @@ template <int LOGM> struct TreePlan {
     static constexpr int TW_TOTAL = TC1 + (NS > 1 ? 8 * T : 0);
 };
 
+// Twiddles of tree depths 0-3 (even nodes).  They do not depend on M, so they are compile-time constants read through the
+// constant bank instead of shared memory (correctly rounded from 200-bit values; identical to TreePlan table entries TA[0..8)).
+__device__ __constant__ double c_tree_ta[16] = {
+    0x1.6a09e667f3bcdp-1, 0x1.6a09e667f3bcdp-1,   // w(0,0)
+    0x1.d906bcf328d46p-1, 0x1.87de2a6aea963p-2,   // w(1,0)
+    0x1.f6297cff75cb0p-1, 0x1.8f8b83c69a60bp-3,   // w(2,0)
+    0x1.1c73b39ae68c8p-1, 0x1.a9b66290ea1a3p-1,   // w(2,2)
+    0x1.fd88da3d12526p-1, 0x1.917a6bc29b42cp-4,   // w(3,0)
+    0x1.44cf325091dd6p-1, 0x1.8bc806b151741p-1,   // w(3,2)
+    0x1.c38b2f180bdb1p-1, 0x1.e2b5d3806f63bp-2,   // w(3,4)
+    0x1.294062ed59f06p-2, 0x1.e9f4156c62ddap-1,   // w(3,6)
+};
+
 template <int T> __device__ __forceinline__ void lanes_sync(int bar_id) {
     if (T == 32) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
@@ -155,7 +168,7 @@ template <int LOGM>
 __device__ __forceinline__ void tree_forward_a(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id) {
     typedef TreePlan<LOGM> P;
     constexpr int T = P::T;
-    pass16<false>(v, tw + P::TA, 1);
+    pass16<false>(v, reinterpret_cast<const cplx*>(c_tree_ta), 1);
     lanes_sync<T>(bar_id);                                   // WAR: earlier reads of buf
 #pragma unroll
     for (int m = 0; m < 16; m++) buf[m * P::S + t] = v[m];
@@ -166,11 +179,15 @@ __device__ __forceinline__ void tree_forward_a(cplx (&v)[16], cplx* __restrict__
     lanes_sync<T>(bar_id);                                   // every lane is done with buf
 }
 template <int LOGM>
-__device__ __forceinline__ void tree_forward_b(cplx (&v)[16], const cplx* __restrict__ tw, const int t) {
+__device__ __forceinline__ void tree_forward_b(cplx (&v)[16], const cplx* __restrict__ tw, const int t) {      // depths 4-7
+    typedef TreePlan<LOGM> P;
+    pass16<false>(v, tw + P::TB + t / P::P, 16);
+}
+template <int LOGM>
+__device__ __forceinline__ void tree_forward_c(cplx (&v)[16], const cplx* __restrict__ tw, const int t) {      // depths 8..
     typedef TreePlan<LOGM> P;
     constexpr int T = P::T;
-    const int b = t / P::P, p = t % P::P;
-    pass16<false>(v, tw + P::TB + b, 16);
+    const int p = t % P::P;
     {   // depth 8
         const bool h = (p >> (P::NS - 1)) & 1;
         half_swap(v, P::P >> 1, h);
@@ -192,6 +209,7 @@ template <int LOGM>
 __device__ __forceinline__ void tree_forward(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id) {
     tree_forward_a<LOGM>(v, buf, tw, t, bar_id);
     tree_forward_b<LOGM>(v, tw, t);
+    tree_forward_c<LOGM>(v, tw, t);
 }
 
 // Backward: the exact mirror.  in v[i] = spectrum slot i ; out v[m] = M * z_{t + T m}
@@ -222,7 +240,7 @@ __device__ __forceinline__ void tree_backward(cplx (&v)[16], cplx* __restrict__ 
     lanes_sync<T>(bar_id);
 #pragma unroll
     for (int m = 0; m < 16; m++) v[m] = buf[m * P::S + t];
-    pass16<true>(v, tw + P::TA, 1);
+    pass16<true>(v, reinterpret_cast<const cplx*>(c_tree_ta), 1);
 }
 
 // ---------------------------------------------------------------------------------------------
