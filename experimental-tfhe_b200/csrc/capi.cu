@@ -476,12 +476,16 @@ int tfhe_b200_CircuitBootstrapFFT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev,
     if ((rc = tfhe_b200_preModSwitch_batch(ctx, abar, pre, count, stream))) return rc;                // :836
     // both mu_w in one pass over bk: boot[B][ell1][N2+1]                                             // :845-847
     if ((rc = cb_woks(ctx, boot, 0, ell1, p.bgbit_lvl1, abar, count, s))) return rc;
-    // result[B][u][w][2][N1]: one private key switch per (u,w) over the whole batch                  // :852-855
-    for (int u = 0; u < 2; u++)
-        for (int w = 0; w < ell1; w++) {
-            int32_t* out = result_dev + ((size_t)(u * ell1 + w) * 2) * N1;
-            if ((rc = cb_privks(ctx, out, 2 * ell1 * 2 * N1, u, boot + (size_t)w * (N2 + 1), ell1 * (N2 + 1), count, s))) return rc;
-        }
+    // result[B][u][w][2][N1]: all four private key switches (u,w) in one launch -- samples are the B*ell1 rows of boot,  // :852-855
+    // grid.z walks u (key and output offset)
+    {
+        KSArgs k{};
+        k.in = boot; k.in_stride = N2 + 1; k.rows_in = N2 + 1; k.t = p.kslength_lvl21; k.basebit = p.ksbasebit_lvl21;
+        k.key = ctx->c_privks; k.cols = 2 * N1; k.cols_pad = 2 * N1; k.b_col = -1; k.b_index = 0;
+        k.out = result_dev; k.count = count * ell1; k.group = ell1; k.out_stride = 2 * ell1 * 2 * N1; k.out_inner = 2 * N1;
+        k.nz = 2; k.key_z_stride = ctx->c_privks_u_stride; k.out_z_stride = (size_t)ell1 * 2 * N1;
+        { ProfScope ps(ctx, 1, s); CU(launch_keyswitch64(k, s)); }
+    }
     return TFHE_B200_OK;
 }
 int tfhe_b200_CircuitBootstrapFFT_batch_host(tfhe_b200_ctx* ctx, int32_t* result_host, const int32_t* sample_host, int count) {

@@ -63,6 +63,10 @@ struct KSArgs {
     int32_t* out;          // [B][out_stride]
     int out_stride;
     int count;
+    // optional (0 = plain): sample s writes to out + (s / group) * out_stride + (s % group) * out_inner ; grid.z = nz
+    // independent keys / outputs (key + z * key_z_stride, out + z * out_z_stride) in one launch
+    int group, out_inner;
+    int nz; size_t key_z_stride, out_z_stride;
 };
 cudaError_t launch_keyswitch32(const KSArgs& a, cudaStream_t s);
 cudaError_t launch_keyswitch64(const KSArgs& a, cudaStream_t s);

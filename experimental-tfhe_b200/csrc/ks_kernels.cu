@@ -4,130 +4,237 @@
 // (cb/poc_CircuitBootstrapping.cpp:437-465) and circuitPrivKS (:667-698):
 //     result = (0,b) - sum_{i<rows, j<t} key[i][j][ d_ij ],   d_ij = ((a_i + prec_offset) >> (W-(j+1)basebit)) & (base-1), d_ij != 0
 // The reference walks the table once per sample (12.3 MB of rows per gate, 147 MB per private key switch).
-// Here a CTA owns a tile of KS_TILE (32) samples x 512 output columns: for every (i,j) it fetches the base-1
-// candidate rows ONCE (coalesced 16-byte loads) and each sample of the tile subtracts the row its digit
-// selects, so table traffic per sample drops by ~KS_TILE*(base-1)/base / (base-1).  Digits are uniform across
-// a warp (all lanes of a warp work on the same samples), so the selection is a uniform branch.
+// Here a CTA owns a tile of KS_TILE (32) samples x 512 output columns: every (i,j) block of base-1 candidate rows
+// arrives ONCE per CTA (TMA bulk copy into a shared-memory ring) and each sample of the tile subtracts the row its
+// digit selects, so table traffic per sample drops by ~KS_TILE.
 //
-// Device key layout: int32 [rows][t][base-1][cols_pad]  (d = 0 rows are never read by the reference either).
+// Device key layout: int32 [cols_pad/512][rows][t][base-1][512]  (d = 0 rows are never read by the reference either).
 #include "engine.h"
+#include "bk_pipe.cuh"
 #include <type_traits>
 #include <cstdlib>
 
 namespace tfhe_b200 {
 
-constexpr int KS_TILE = 32;     // samples per CTA
-constexpr int KS_S = 8;         // samples per thread
-constexpr int KS_ICHUNK = 32;   // input coefficients staged per shared-memory refill
+#ifndef KS_S_DEF
+#define KS_S_DEF 8
+#endif
+#ifndef KS_CTAS
+#define KS_CTAS 2
+#endif
+constexpr int KS_S = KS_S_DEF;    // samples per thread
+constexpr int KS_TILE = 4 * KS_S; // samples per CTA
+constexpr int KS_ICHUNK = 32;     // input coefficients staged per refill of a warp's digit source
+constexpr int KS_WARPS = 8;       // 4 sample groups x 2 column halves
+constexpr int KS_THREADS = KS_WARPS * 32;
 
-// Thread layout: 64 column groups (8 consecutive int32 columns = two int4 each) x 4 sample groups (8 samples each).
-// A warp is 32 column groups of ONE sample group, so a sample's digit is warp-uniform and picking the row is a uniform branch.
-// 8 columns per thread (instead of 4) halves the per-add overhead of digit extraction and branching (profiles/r1_notes.md).
+template <int BASEBIT> struct KSCfg {
+    static constexpr int BASE = 1 << BASEBIT;
+    static constexpr int STAGE_INTS = (BASE - 1) * 512;            // one (i,j) block: the base-1 candidate rows of this CTA's 512 columns
+    static constexpr int STAGE_BYTES = STAGE_INTS * 4;
+    static constexpr int NSTAGE = BASEBIT == 3 ? 6 : (BASEBIT == 2 ? 10 : 16);
+    // rows are copied to registers and selected by a warp-uniform branch while base-1 < KS_S; for base 8 there are as many
+    // rows as samples per thread, so each sample reads the row it selects straight from the ring instead.
+    static constexpr bool ROWS_IN_REGS = BASEBIT <= 2;
+};
+template <typename U, int BASEBIT> constexpr size_t ks_smem_bytes() {
+    return (size_t)KSCfg<BASEBIT>::NSTAGE * KSCfg<BASEBIT>::STAGE_BYTES + 2 * KSCfg<BASEBIT>::NSTAGE * sizeof(uint64_t) +
+           (size_t)KS_WARPS * KS_S * (KS_ICHUNK + 1) * sizeof(U) + 128;
+}
+
+__device__ __forceinline__ void sub8(int4& a0, int4& a1, const int4& r0, const int4& r1) {
+    a0.x -= r0.x; a0.y -= r0.y; a0.z -= r0.z; a0.w -= r0.w;
+    a1.x -= r1.x; a1.y -= r1.y; a1.z -= r1.z; a1.w -= r1.w;
+}
+
+__device__ __forceinline__ uint32_t smem_inc_acq_rel(uint32_t* p) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
+    return old;
+}
+
+// The key is one linear stream per 512-column group ([group][i][j][d][512] int32), walked identically by every CTA of that
+// group.  It is pulled into a shared-memory ring with 1-D TMA bulk copies, NSTAGE blocks ahead of its use.  There is no
+// producer warp and no CTA-wide barrier in the loop: each warp counts itself out of a slot when it has read it (an atomic
+// whose result is only looked at after the block's arithmetic, so its round trip is hidden), and the LAST of the 8 warps
+// to leave re-arms the slot's mbarrier and issues the copy of the block NSTAGE further down the stream.
+// (Letting a fixed warp issue the refill after waiting on an `empty` mbarrier was 2x slower: the issuer waits for the
+// slowest warp and every other warp then starves behind the late refill -- profiles/r1_notes.md.)
+// Warp w owns sample group w>>1 (8 samples, so a sample's digit is warp-uniform and selecting its row is a uniform branch /
+// a uniform address) and column half w&1; lane l accumulates columns [4l,4l+4) and [128+4l,128+4l+4) of that half -- two
+// conflict-free LDS.128 per row.
 template <typename TorusIn, int BASEBIT>
-__global__ void __launch_bounds__(256, 2) keyswitch_kernel(const KSArgs A) {
+__global__ void __launch_bounds__(KS_THREADS, KS_CTAS) keyswitch_kernel(const KSArgs A) {
     typedef typename std::conditional<sizeof(TorusIn) == 4, uint32_t, uint64_t>::type U;
+    typedef KSCfg<BASEBIT> C;
     constexpr int W = sizeof(TorusIn) * 8;
-    constexpr int BASE = 1 << BASEBIT;
-    __shared__ U abar[KS_TILE][KS_ICHUNK + 1];
+    constexpr int BASE = C::BASE;
+    extern __shared__ __align__(128) unsigned char ks_smem[];
+    int4* ring = reinterpret_cast<int4*>(ks_smem);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ks_smem + (size_t)C::NSTAGE * C::STAGE_BYTES);
+    uint32_t* left = reinterpret_cast<uint32_t*>(full + C::NSTAGE);          // warps that have left each slot
+    U* abar_all = reinterpret_cast<U*>(full + 2 * C::NSTAGE);
 
-    const int cg = threadIdx.x & 63;            // column group: columns [8 cg, 8 cg + 8) of this CTA's 512-column slice
-    const int sg = threadIdx.x >> 6;            // sample group
-    const int s0 = blockIdx.x * KS_TILE;        // first sample of the tile
-    const int col0 = blockIdx.y * 512 + cg * 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nblk = A.rows_in * A.t;
+    const int32_t* kstream = A.key + (size_t)blockIdx.z * A.key_z_stride + (size_t)blockIdx.y * nblk * C::STAGE_INTS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::NSTAGE; s++) { mbar_init(full + s, 1); left[s] = 0; }
+        mbar_fence_init();
+        for (int s = 0; s < C::NSTAGE && s < nblk; s++) {
+            mbar_expect_tx(full + s, C::STAGE_BYTES);
+            tma_load_1d(reinterpret_cast<unsigned char*>(ring) + (size_t)s * C::STAGE_BYTES, kstream + (size_t)s * C::STAGE_INTS, C::STAGE_BYTES, full + s);
+        }
+    }
+    __syncthreads();
+
+    const int sg = warp >> 1, half = warp & 1;
+    const int s0 = blockIdx.x * KS_TILE + sg * KS_S;              // this warp's first sample
     const TorusIn* in = reinterpret_cast<const TorusIn*>(A.in);
     const U prec_offset = (U)1 << (W - (1 + BASEBIT * A.t));      // cb/lwe_functions.cpp:141 ; poc:444,674
+    U (*abar)[KS_ICHUNK + 1] = reinterpret_cast<U (*)[KS_ICHUNK + 1]>(abar_all + (size_t)warp * KS_S * (KS_ICHUNK + 1));
+    const int lofs = half * 64 + lane;                            // int4 index of this lane's first column quad inside a row
 
     int4 acc0[KS_S], acc1[KS_S];
 #pragma unroll
     for (int s = 0; s < KS_S; s++) { acc0[s] = make_int4(0, 0, 0, 0); acc1[s] = make_int4(0, 0, 0, 0); }
 
-    const size_t rs4 = (size_t)A.cols_pad / 4;                    // one key row, in int4
-    const int4* key4 = reinterpret_cast<const int4*>(A.key + col0);
+    // leave(): count this warp out of a slot (after its reads of the slot have been issued); refill_if_last(): the warp
+    // that counted out last refills the slot with the block NSTAGE further on.
+    auto leave = [&](int slot) -> uint32_t {
+        uint32_t tok = 0;
+        __syncwarp();
+        if (lane == 0) tok = smem_inc_acq_rel(left + slot);
+        return tok;
+    };
+    auto refill_if_last = [&](uint32_t tok, int slot, int k) {
+        if (tok == KS_WARPS - 1) {                                // lane 0 of the last warp out
+            left[slot] = 0;
+            const int kn = k + C::NSTAGE;
+            if (kn < nblk) {
+                fence_proxy_async_smem();
+                mbar_expect_tx(full + slot, C::STAGE_BYTES);
+                tma_load_1d(reinterpret_cast<unsigned char*>(ring) + (size_t)slot * C::STAGE_BYTES, kstream + (size_t)kn * C::STAGE_INTS,
+                            C::STAGE_BYTES, full + slot);
+            }
+        }
+    };
 
+    int slot = 0, k = 0; uint32_t ph = 0;
     for (int i0 = 0; i0 < A.rows_in; i0 += KS_ICHUNK) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < KS_ICHUNK * KS_TILE; e += 256) {
-            const int ii = e % KS_ICHUNK, s = e / KS_ICHUNK;      // consecutive threads read consecutive coefficients
-            const int smp = s0 + s, i = i0 + ii;
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < KS_S; s++) {                          // lane = coefficient index: 128/256-byte coalesced rows
+            const int smp = s0 + s, i = i0 + lane;
             U v = 0;
             if (smp < A.count && i < A.rows_in) v = (U)in[(size_t)smp * A.in_stride + i] + prec_offset;
-            abar[s][ii] = v;
+            abar[s][lane] = v;
         }
-        __syncthreads();
+        __syncwarp();
         const int iend = min(KS_ICHUNK, A.rows_in - i0);
         for (int ii = 0; ii < iend; ii++) {
             U a[KS_S];
 #pragma unroll
-            for (int s = 0; s < KS_S; s++) a[s] = abar[sg * KS_S + s][ii];
-            const int4* krow = key4 + ((size_t)(i0 + ii) * A.t) * (BASE - 1) * rs4;
-            for (int j = 0; j < A.t; j++) {
+            for (int s = 0; s < KS_S; s++) a[s] = abar[s][ii];
+            for (int j = 0; j < A.t; j++, k++) {
                 const int sh = W - (j + 1) * BASEBIT;
-                int4 r0[BASE - 1], r1[BASE - 1];
+                int dg[KS_S];
 #pragma unroll
-                for (int d = 0; d < BASE - 1; d++) {
-                    const int4* rp = krow + ((size_t)j * (BASE - 1) + d) * rs4;
-                    r0[d] = __ldg(rp); r1[d] = __ldg(rp + 1);
-                }
+                for (int s = 0; s < KS_S; s++) dg[s] = (int)((a[s] >> sh) & (U)(BASE - 1));
+                const int4* st = ring + (size_t)slot * (C::STAGE_INTS / 4) + lofs;
+                while (!mbar_try_wait(full + slot, ph)) {}
+                if constexpr (C::ROWS_IN_REGS) {
+                    int4 r0[BASE - 1], r1[BASE - 1];
 #pragma unroll
-                for (int s = 0; s < KS_S; s++) {
-                    const int dg = (int)((a[s] >> sh) & (U)(BASE - 1));
+                    for (int d = 0; d < BASE - 1; d++) { r0[d] = st[d * 128]; r1[d] = st[d * 128 + 32]; }
+                    const uint32_t tok = leave(slot);             // rows are in registers: the slot can be refilled already
 #pragma unroll
-                    for (int d = 0; d < BASE - 1; d++) {
-                        if (dg == d + 1) {
-                            acc0[s].x -= r0[d].x; acc0[s].y -= r0[d].y; acc0[s].z -= r0[d].z; acc0[s].w -= r0[d].w;
-                            acc1[s].x -= r1[d].x; acc1[s].y -= r1[d].y; acc1[s].z -= r1[d].z; acc1[s].w -= r1[d].w;
+                    for (int s = 0; s < KS_S; s++) {
+#pragma unroll
+                        for (int d = 0; d < BASE - 1; d++)
+                            if (dg[s] == d + 1) sub8(acc0[s], acc1[s], r0[d], r1[d]);
+                    }
+                    refill_if_last(tok, slot, k);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < KS_S; s++) {
+                        if (dg[s] != 0) {
+                            const int4* rp = st + (dg[s] - 1) * 128;
+                            sub8(acc0[s], acc1[s], rp[0], rp[32]);
                         }
                     }
+                    refill_if_last(leave(slot), slot, k);
                 }
+                if (++slot == C::NSTAGE) { slot = 0; ph ^= 1; }
             }
         }
     }
     // result starts as the noiseless trivial sample (0,b) (cb/lwe_functions.cpp:169) or 0 (poc:677-681)
+    const int colbase = blockIdx.y * 512 + half * 256 + lane * 4;
 #pragma unroll
     for (int s = 0; s < KS_S; s++) {
-        const int smp = s0 + sg * KS_S + s;
+        const int smp = s0 + s;
         if (smp >= A.count) continue;
+        int32_t* orow = A.out + (size_t)blockIdx.z * A.out_z_stride + (size_t)(smp / A.group) * A.out_stride + (size_t)(smp % A.group) * A.out_inner;
         const int v[8] = {acc0[s].x, acc0[s].y, acc0[s].z, acc0[s].w, acc1[s].x, acc1[s].y, acc1[s].z, acc1[s].w};
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            const int col = col0 + c;
+            const int col = colbase + (c & 3) + (c >> 2) * 128;
             if (col < A.cols) {
                 int32_t x = v[c];
                 if (col == A.b_col) x += (int32_t)in[(size_t)smp * A.in_stride + A.b_index];
-                A.out[(size_t)smp * A.out_stride + col] = x;
+                orow[col] = x;
             }
         }
     }
 }
 
+template <typename TorusIn, int BASEBIT>
+static cudaError_t launch_ks_b(const KSArgs& a, cudaStream_t s) {
+    typedef typename std::conditional<sizeof(TorusIn) == 4, uint32_t, uint64_t>::type U;
+    constexpr size_t smem = ks_smem_bytes<U, BASEBIT>();
+    static bool attr_done = false;               // per instantiation
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(keyswitch_kernel<TorusIn, BASEBIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(keyswitch_kernel<TorusIn, BASEBIT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((a.count + KS_TILE - 1) / KS_TILE, a.cols_pad / 512, a.nz > 0 ? a.nz : 1);
+    keyswitch_kernel<TorusIn, BASEBIT><<<grid, KS_THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
 template <typename TorusIn>
-static cudaError_t launch_ks(const KSArgs& a, cudaStream_t s) {
+static cudaError_t launch_ks(KSArgs a, cudaStream_t s) {
     if (a.count <= 0) return cudaSuccess;
     if (a.cols_pad % 512) return cudaErrorInvalidValue;
-    dim3 grid((a.count + KS_TILE - 1) / KS_TILE, a.cols_pad / 512);
+    if (a.group <= 0) { a.group = 1; a.out_inner = 0; }
     switch (a.basebit) {
-        case 1: keyswitch_kernel<TorusIn, 1><<<grid, 256, 0, s>>>(a); break;
-        case 2: keyswitch_kernel<TorusIn, 2><<<grid, 256, 0, s>>>(a); break;
-        case 3: keyswitch_kernel<TorusIn, 3><<<grid, 256, 0, s>>>(a); break;
+        case 1: return launch_ks_b<TorusIn, 1>(a, s);
+        case 2: return launch_ks_b<TorusIn, 2>(a, s);
+        case 3: return launch_ks_b<TorusIn, 3>(a, s);
         default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 cudaError_t launch_keyswitch32(const KSArgs& a, cudaStream_t s) { return launch_ks<int32_t>(a, s); }
 cudaError_t launch_keyswitch64(const KSArgs& a, cudaStream_t s) { return launch_ks<int64_t>(a, s); }
 
-// raw [rows][t][base][cols] -> [rows][t][base-1][cols_pad]  (zero padded)
-__global__ void ks_repack_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, size_t nrows_out, int base, int cols, int cols_pad) {
-    const size_t total = nrows_out * (size_t)cols_pad;
+// raw [rows][t][base][cols] -> [cols_pad/512][rows][t][base-1][512]  (d = 0 dropped, zero padded)
+__global__ void ks_repack_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, size_t nblk, int base, int cols, int cols_pad) {
+    const size_t per_group = nblk * (size_t)(base - 1) * 512;
+    const size_t total = per_group * (size_t)(cols_pad / 512);
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const size_t ro = e / cols_pad; const int c = (int)(e % cols_pad);
+        const size_t g = e / per_group, r = e % per_group;
+        const int c = (int)(g * 512 + r % 512);
+        const size_t ro = r / 512;
         const size_t ij = ro / (base - 1); const int d = (int)(ro % (base - 1)) + 1;
         dst[e] = c < cols ? src[(ij * base + d) * (size_t)cols + c] : 0;
     }
 }
 cudaError_t launch_ks_repack(int32_t* dst, const int32_t* src, int rows, int t, int base, int cols, int cols_pad, cudaStream_t s) {
-    const size_t nrows_out = (size_t)rows * t * (base - 1);
-    ks_repack_kernel<<<148 * 8, 256, 0, s>>>(dst, src, nrows_out, base, cols, cols_pad);
+    ks_repack_kernel<<<148 * 8, 256, 0, s>>>(dst, src, (size_t)rows * t, base, cols, cols_pad);
     return cudaGetLastError();
 }
 

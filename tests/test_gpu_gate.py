@@ -197,3 +197,31 @@ def test_errors_are_loud(engine):
     with pytest.raises(mod.EngineError):
         fresh.load_gate_keys(dict(n=500, N=512, k=1, bk_l=2, bk_Bgbit=10, ks_t=8, ks_basebit=2), np.zeros(4, np.int32), np.zeros(4, np.int32))
     fresh.close()
+
+
+def test_full_batch_65536_nand_decrypts(gate_engine, gate_oracle):
+    """BASELINE configs[1] at full size: 65,536 bootsNAND on real encryptions of random bits; every output decrypts to
+    NAND(a, b) (size-independent property: the oracle cannot run 65,536 bootstraps in seconds, decryption can)."""
+    g = gate_oracle
+    B = 65536
+    rng = np.random.default_rng(2026)
+    a = rng.integers(0, 2, size=B); b = rng.integers(0, 2, size=B)
+    # fresh encryptions: a random mask plus b = phase + <a, s>  (cb/lwe_functions.cpp:43-54), vectorised
+    key = g.lwe_key.astype(np.int64)
+    def enc(bits, seed):
+        r = np.random.default_rng(seed)
+        mask = r.integers(-2**31, 2**31 - 1, size=(B, g.n), dtype=np.int64)
+        noise = np.rint(r.normal(0.0, g.params.ks_stdev, size=B) * 2.0**32).astype(np.int64)
+        body = (np.where(bits == 1, g.MU, -g.MU) + noise + mask @ key) & 0xFFFFFFFF
+        out = np.empty((B, g.n + 1), np.int64); out[:, :g.n] = mask & 0xFFFFFFFF; out[:, g.n] = body
+        return out.astype(np.uint32).view(np.int32)
+    ca, cb = enc(a, 1), enc(b, 2)
+    out = torch.empty((B, g.n + 1), dtype=torch.int32, device=DEV)
+    gate_engine.bootsNAND(out, dev(ca), dev(cb), B)
+    torch.cuda.synchronize()
+    res = out.cpu().numpy().astype(np.int64)
+    phase = (res[:, g.n] - res[:, :g.n] @ key) & 0xFFFFFFFF
+    phase = np.where(phase >= 2**31, phase - 2**32, phase)
+    assert np.array_equal((phase > 0).astype(np.int64), 1 - (a & b))
+    err = phase - np.where((1 - (a & b)) == 1, g.MU, -g.MU)
+    assert np.abs(err).max() < 2**28          # 1/16 of the torus: far from the decision boundary
