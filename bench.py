@@ -242,6 +242,15 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        # DRAM bytes per launch of the blind-rotation kernel, from the committed ncu --set full capture of this same command
+        # (profiles/r1_traffic.json says which report); only quoted when the capture was taken at this batch size
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["blind_rotate_kernel"]
+            if tr["batch"] == B:
+                traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -253,7 +262,7 @@ def main():
             "gpu_launches": launches,
             "kernel_ms_per_step": {k: v / args.steps for k, v in kern_ms.items()},
             "roofline": {"bound": "fp64", "kernel": "blind_rotate_kernel<9,int32_t>", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "DFMA probe measured in this run (nominal 37.2 at 1965 MHz)",
                          "algorithmic": "94.72 MFLOP per gate bootstrap x gates per launch (SURVEY 8d)",
                          "l2_read_gbs_measured": l2_gbs},
