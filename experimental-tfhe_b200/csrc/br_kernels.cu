@@ -68,10 +68,12 @@ __device__ __forceinline__ int modswitch32(int32_t x, int log2Msize) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"       \
                  ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), \
                    "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(addr) : "memory")
-#define TFHE_TLD4(r, addr) \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory")
-#define TFHE_TST4(r, addr) \
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(addr) : "memory")
+#define TFHE_TLD8(r, addr)                                                                                                \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                   \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr) : "memory")
+#define TFHE_TST8(r, addr)                                                                                                \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"                                   \
+                 ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(addr) : "memory")
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -144,18 +146,22 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
 }
 
 // One CMUX: ACC <- ACC + BK_i (x) ((X^a - 1) ACC).   acc: shared [2][N].  bk: BK_i = [2l][2][M] spectra (scaled 2/N).
-// PACK2 (l == 2): both gadget digits of a coefficient come from ONE rotated read of the accumulator; the second-level digits
-// wait, packed two per word, in 16 TMEM columns of this lane.  Otherwise the accumulator is re-read per level.
-template <int LOGM, typename Torus, bool PACK2, bool ALLREG>
+// STASH: the rotated difference u = (X^a - 1) ACC_q + offset of a coefficient is formed ONCE per q (level 0: two shared-memory
+// reads, index and sign arithmetic) and parked in this lane's tensor-memory columns [128, 128 + 32 words); levels 1.. only
+// reload it and cut their digit.  Otherwise every level re-reads the accumulator.
+template <typename Torus> struct StashWords { static constexpr int PER_C = 8 * (int)(sizeof(Torus) / 4); };   // words per c (4 complex)
+template <int LOGM, typename Torus, bool STASH, bool ALLREG>
 __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, const cplx* __restrict__ bk,
                                           const int l, const int Bgbit, cplx* __restrict__ buf, const uint32_t tacc,
                                           BkSlot& s0, const cplx* __restrict__ tw, const int t, const int bar_id) {
     typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
     constexpr int M = P::M, N = P::N, T = P::T, W = TorusTraits<Torus>::W;
+    constexpr int WPC = StashWords<Torus>::PER_C;
     const U offset = decomp_offset((U)0, l, Bgbit);
     const uint32_t mask = (1u << Bgbit) - 1u;
     const int half = 1 << (Bgbit - 1);
+    const bool stash = STASH && l > 1;
 
 #pragma unroll 1
     for (int p = 0; p < 2 * l; p++) {
@@ -163,21 +169,31 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
         const Torus* __restrict__ aq = acc + q * N;
         const int sh = W - (lev + 1) * Bgbit;
         cplx v[16];
-        if (PACK2 && lev == 1) {
+        if (STASH && lev > 0) {
+            uint32_t w[4][WPC];
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                uint32_t pk[4];
-                TFHE_TLD4(pk, tacc + 128 + 4 * c);
-                tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 4; i++) v[4 * c + i] = make_double2((double)((int)(pk[i] << 16) >> 16), (double)((int)pk[i] >> 16));
+                if constexpr (WPC == 8) { TFHE_TLD8(w[c], tacc + 128 + WPC * c); }
+                else                    { TFHE_TLD16(w[c], tacc + 128 + WPC * c); }
             }
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    U ure, uim;
+                    if (WPC == 8) { ure = (U)w[c][2 * i]; uim = (U)w[c][2 * i + 1]; }
+                    else { ure = (U)(((uint64_t)w[c][(4 * i + 1) % WPC] << 32) | w[c][(4 * i) % WPC]);
+                           uim = (U)(((uint64_t)w[c][(4 * i + 3) % WPC] << 32) | w[c][(4 * i + 2) % WPC]); }
+                    v[4 * c + i] = make_double2((double)((int)((uint32_t)(ure >> sh) & mask) - half),
+                                                (double)((int)((uint32_t)(uim >> sh) & mask) - half));
+                }
         } else {
             int a2 = a;
             asm volatile("" : "+r"(a2));          // keep the 32 rotated addresses from being hoisted out of the loop
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                uint32_t pk[4];
+                uint32_t w[WPC];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int j = t + T * (4 * c + i);
@@ -185,15 +201,18 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
                     const U uim = (U)rot_minus_one<Torus, N>(aq, j + M, a2) + offset;
                     v[4 * c + i] = make_double2((double)((int)((uint32_t)(ure >> sh) & mask) - half),
                                                 (double)((int)((uint32_t)(uim >> sh) & mask) - half));
-                    if (PACK2) {
-                        const uint32_t d1r = (uint32_t)((int)((uint32_t)(ure >> (sh - Bgbit)) & mask) - half);
-                        const uint32_t d1i = (uint32_t)((int)((uint32_t)(uim >> (sh - Bgbit)) & mask) - half);
-                        pk[i] = (d1r & 0xFFFFu) | (d1i << 16);
+                    if (STASH) {
+                        if (WPC == 8) { w[(2 * i) % WPC] = (uint32_t)ure; w[(2 * i + 1) % WPC] = (uint32_t)uim; }
+                        else { w[(4 * i) % WPC] = (uint32_t)ure; w[(4 * i + 1) % WPC] = (uint32_t)((uint64_t)ure >> 32);
+                               w[(4 * i + 2) % WPC] = (uint32_t)uim; w[(4 * i + 3) % WPC] = (uint32_t)((uint64_t)uim >> 32); }
                     }
                 }
-                if (PACK2) TFHE_TST4(pk, tacc + 128 + 4 * c);
+                if (stash) {
+                    if constexpr (WPC == 8) { TFHE_TST8(w, tacc + 128 + WPC * c); }
+                    else                    { TFHE_TST16(w, tacc + 128 + WPC * c); }
+                }
             }
-            if (PACK2) tmem_wait_st();
+            if (stash) tmem_wait_st();
         }
         if (p == 0) forward_and_mac<LOGM, true, ALLREG>(v, tacc, bk, buf, s0, tw, t, bar_id);
         else        forward_and_mac<LOGM, false, ALLREG>(v, tacc, bk + (size_t)(p * 2) * M, buf, s0, tw, t, bar_id);
@@ -235,7 +254,8 @@ template <int LOGM, typename Torus, int GROUPS> struct BRSmem {
     static constexpr int WARPS = GROUPS * P::T / 32;
     static_assert(sizeof(cplx) * P::BUF >= sizeof(cplx) * P::M, "transpose buffer must hold one key polynomial");
     static_assert(TOTAL <= 232448, "shared memory budget (227 KB) exceeded");
-    static_assert((WARPS + 3) / 4 * 144 <= 512, "tensor memory: 144 columns per warp, 4 lane quarters");
+    static constexpr int TMEM_COLS = 128 + 4 * StashWords<Torus>::PER_C;               // R0 (64) | R1 (64) | stash of u (32 words)
+    static_assert((WARPS + 3) / 4 * TMEM_COLS <= 512, "tensor memory: TMEM_COLS columns per warp, 4 lane quarters");
 };
 
 // rotation amount i of sample ct (i == n: the b part), straight from the kernel's inputs -- nothing is staged in shared memory
@@ -257,7 +277,7 @@ __device__ __forceinline__ int fetch_bara(const BRArgs& A, const int ct, const i
     return __ldg(A.bara + (size_t)ct * n + i);
 }
 
-template <int LOGM, typename Torus, int GROUPS, bool PACK2, bool ALLREG>
+template <int LOGM, typename Torus, int GROUPS, bool STASH, bool ALLREG>
 __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_kernel(const BRArgs A) {
     typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
@@ -283,7 +303,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_base_slot;
-    const uint32_t tacc = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 144u;   // R0 | R1 | packed digits
+    const uint32_t tacc = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)S::TMEM_COLS;   // R0 | R1 | stash
     BkSlot s0{&bars[0], reinterpret_cast<unsigned char*>(buf), 0u};
 
     // unit = (sample, test-vector index); n_mu > 1 only on the circuit-bootstrap path
@@ -292,7 +312,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
     if (unit < (long)A.count * n_mu) {                 // idle groups of the last CTA fall through to the final barrier
         const int ct = (int)(unit / n_mu), w = (int)(unit % n_mu);
         const int n = A.n;
-        const int l = PACK2 ? 2 : A.l;
+        const int l = A.l;
 
         // ---- the initial accumulator
         Torus mu = (Torus)A.mu;
@@ -326,7 +346,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
             const int a = a_next;
             if (i + 1 < n) a_next = fetch_bara<LOGM, Torus>(A, ct, i + 1);
             if (a == 0) continue;
-            cmux_step<LOGM, Torus, PACK2, ALLREG>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, s0, tw, t, bar_id);
+            cmux_step<LOGM, Torus, STASH, ALLREG>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, s0, tw, t, bar_id);
         }
 
         // ---- epilogue
@@ -354,14 +374,14 @@ static bool g_inited = false;
 // fastest (166 k bootstraps/s); 12 warps with BK[p][0] landing in shared memory by TMA is kept for comparison (146 k/s).
 constexpr int G32 = 8, G32_TMA = 12, G64 = 4;     // accumulators per CTA (N=1024: one warp each; N=2048: two warps each)
 
-template <int LOGM, typename Torus, int GROUPS, bool PACK2, bool ALLREG> static cudaError_t br_attr() {
-    return cudaFuncSetAttribute(blind_rotate_kernel<LOGM, Torus, GROUPS, PACK2, ALLREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int LOGM, typename Torus, int GROUPS, bool STASH, bool ALLREG> static cudaError_t br_attr() {
+    return cudaFuncSetAttribute(blind_rotate_kernel<LOGM, Torus, GROUPS, STASH, ALLREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)BRSmem<LOGM, Torus, GROUPS>::TOTAL);
 }
 cudaError_t blind_rotate_init() {
     cudaError_t e;
+    if ((e = br_attr<9, int32_t, G32, true, true>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32, false, true>()) != cudaSuccess) return e;
-    if ((e = br_attr<9, int32_t, G32_TMA, false, false>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32_TMA, true, false>()) != cudaSuccess) return e;
     if ((e = br_attr<10, int64_t, G64, false, true>()) != cudaSuccess) return e;
     g_inited = true;
@@ -371,17 +391,17 @@ cudaError_t blind_rotate_init() {
 cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
     if (!g_inited) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
     if (a.count <= 0) return cudaSuccess;
-    // development knob: TFHE_B200_BR_VARIANT = tma | tma_pack selects the measured alternatives
+    // development knob: TFHE_B200_BR_VARIANT = nostash | tma selects the measured alternatives
     static const char* variant = getenv("TFHE_B200_BR_VARIANT");
     if (variant && variant[0] == 't') {
         const int grid = (a.count + G32_TMA - 1) / G32_TMA;
-        if (a.l == 2 && variant[3] == '_')
-            blind_rotate_kernel<9, int32_t, G32_TMA, true, false><<<grid, G32_TMA * TreePlan<9>::T, BRSmem<9, int32_t, G32_TMA>::TOTAL, s>>>(a);
-        else
-            blind_rotate_kernel<9, int32_t, G32_TMA, false, false><<<grid, G32_TMA * TreePlan<9>::T, BRSmem<9, int32_t, G32_TMA>::TOTAL, s>>>(a);
-    } else {
+        blind_rotate_kernel<9, int32_t, G32_TMA, true, false><<<grid, G32_TMA * TreePlan<9>::T, BRSmem<9, int32_t, G32_TMA>::TOTAL, s>>>(a);
+    } else if (variant && variant[0] == 'n') {
         const int grid = (a.count + G32 - 1) / G32;
         blind_rotate_kernel<9, int32_t, G32, false, true><<<grid, G32 * TreePlan<9>::T, BRSmem<9, int32_t, G32>::TOTAL, s>>>(a);
+    } else {
+        const int grid = (a.count + G32 - 1) / G32;
+        blind_rotate_kernel<9, int32_t, G32, true, true><<<grid, G32 * TreePlan<9>::T, BRSmem<9, int32_t, G32>::TOTAL, s>>>(a);
     }
     return cudaGetLastError();
 }
@@ -390,6 +410,8 @@ cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
     if (a.count <= 0) return cudaSuccess;
     const long units = (long)a.count * (a.n_mu > 0 ? a.n_mu : 1);
     const int grid = (int)((units + G64 - 1) / G64);
+    // no stash for Torus64: 64 columns of u per lane cost more tensor-memory traffic than the re-reads save (232 vs 225 ms
+    // per 4096 circuit bootstraps, profiles/r1_notes.md)
     blind_rotate_kernel<10, int64_t, G64, false, true><<<grid, G64 * TreePlan<10>::T, BRSmem<10, int64_t, G64>::TOTAL, s>>>(a);
     return cudaGetLastError();
 }
