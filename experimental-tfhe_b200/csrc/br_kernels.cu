@@ -447,9 +447,14 @@ __global__ void __launch_bounds__(256) poly_to_spectrum_kernel(cplx* __restrict_
         v[m] = make_double2((double)src[j], (double)src[j + M]);
     }
     tree_forward<LOGM>(v, buf, tw, t, 1 + g);
+    // the stored spectrum is the TRUE one: divide the per-slot unit factor of the select-free exchange out (TreePlan::TG)
     cplx* dst = out + (size_t)poly * M + t;
+    const cplx* gf = twg + P::TG + t;
 #pragma unroll
-    for (int i = 0; i < 16; i++) dst[i * T] = make_double2(v[i].x * scale, v[i].y * scale);
+    for (int i = 0; i < 16; i++) {
+        const cplx gi = gf[i * T];          // v * conj(g) * scale
+        dst[i * T] = make_double2((v[i].x * gi.x + v[i].y * gi.y) * scale, (v[i].y * gi.x - v[i].x * gi.y) * scale);
+    }
 }
 
 template <int LOGM, typename Torus>
@@ -468,7 +473,12 @@ __global__ void __launch_bounds__(256) spectrum_to_torus_kernel(Torus* __restric
     const cplx* src = in + (size_t)poly * M + t;
     cplx v[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) { cplx x = src[i * T]; v[i] = make_double2(x.x * scale, x.y * scale); }   // 2/N pre-scale (:78-100)
+    const cplx* gf = twg + P::TG + t;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {          // 2/N pre-scale (:78-100), times the slot's unit factor g the backward tree expects
+        const cplx x = src[i * T], gi = gf[i * T];
+        v[i] = make_double2((x.x * gi.x - x.y * gi.y) * scale, (x.x * gi.y + x.y * gi.x) * scale);
+    }
     tree_backward<LOGM>(v, buf, tw, t, 1 + g);
     Torus* dst = out + (size_t)poly * N;
 #pragma unroll

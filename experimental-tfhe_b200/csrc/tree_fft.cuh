@@ -66,11 +66,23 @@ __device__ __forceinline__ void bf_inv_i(cplx& lo, cplx& hi, const cplx w) {
 
 // ---------------------------------------------------------------------------------------------
 // Geometry and twiddle-table layout (cplx entries), LOGM = log2(M) in {9, 10}
-//   TA  [8]        depths 0-3, essential (even) nodes: (0,0) (1,0) (2,0) (2,2) (3,0) (3,2) (3,4) (3,6)
-//   TB  [8][16]    depths 4-7 under depth-4 node b: (4,b) (5,2b) (6,4b) (6,4b+2) (7,8b+2k), k<4     index e*16+b
-//   TC0 [4][M/16]  depth 8, lane group g: nodes 8g+2k, k<4                                         index k*(M/16)+g
-//   TC1 [8][T]     depth 9 (M=1024 only), lane t: nodes 16(t>>1)+2k+(t&1), k<8                     index k*T+t
+//   TA  [8]          depths 0-3, essential (even) nodes: (0,0) (1,0) (2,0) (2,2) (3,0) (3,2) (3,4) (3,6)
+//   TB  [2][8][16]   depths 4-7 under depth-4 node b: (4,b) (5,2b) (6,4b) (6,4b+2) (7,8b+2k), k<4    index h*128+e*16+b
+//                    h = the lane's side in the first exchange; for h = 1 the depth-7 entries are NEGATED
+//   TC0 [8][T]       depth 8, per lane                                                             index m*T+t
+//   TC1 [8][T]       depth 9 (M=1024 only), per lane                                               index m*T+t
+//   TG  [16][T]      unit factors g carried by the slots of a lane (global memory only; standalone transforms)
 //   node twiddle w(d,nu) = exp(2 pi i (1 + 4 bitrev_d(nu)) / 2^(d+3))
+//
+// Select-free lane exchange (numpy model and derivation: tools/tree_fft_model.py).  After depths 4-7 a lane holds ONE
+// coefficient of 16 depth-8 nodes; the depth-8 butterfly needs (lo, hi) from two lanes.  The exchange always sends the
+// odd registers v[2m+1] and receives into them, on both sides -- no per-register selects.  To make that work, lanes on
+// side h = 1 run depth 7 with negated twiddles (their two outputs land swapped), so after the exchange side 0 owns
+// (lo, hi) of node 16b+2m and side 1 owns (hi, lo) of node 16b+2m+1; side 1 then uses conj(w) as its depth-8 twiddle and
+// obtains conj(w)*plus and -conj(w)*minus: the true outputs times a unit factor g that depends only on (lane, slot).
+// Digit spectra and the spectral accumulators of a blind rotation carry the same g, the key spectra are stored TRUE, so the
+// multiply-accumulate needs no correction and the backward transform (same tables, mirrored) removes g exactly.
+// For M = 1024 the second exchange repeats the construction (depth-8 twiddles negated on its side-1 lanes).
 // ---------------------------------------------------------------------------------------------
 template <int LOGM> struct TreePlan {
     static constexpr int M = 1 << LOGM;
@@ -80,12 +92,13 @@ template <int LOGM> struct TreePlan {
     static constexpr int NS = LOGM - 8;            // shuffle stages
     static constexpr int S = T + T / 16;           // padded row stride of the transpose buffer
     static constexpr int BUF = 16 * S;             // cplx entries per polynomial
-    static constexpr int G0 = T >> (NS - 1);       // lane groups at depth 8 (= 32 for both sizes)
     static constexpr int TA = 0;
     static constexpr int TB = 8;
-    static constexpr int TC0 = TB + 128;
-    static constexpr int TC1 = TC0 + 4 * G0;
-    static constexpr int TW_TOTAL = TC1 + (NS > 1 ? 8 * T : 0);
+    static constexpr int TC0 = TB + 256;
+    static constexpr int TC1 = TC0 + 8 * T;
+    static constexpr int TW_TOTAL = TC1 + (NS > 1 ? 8 * T : 0);      // what the kernels keep in shared memory
+    static constexpr int TG = TW_TOTAL;
+    static constexpr int TABLE_ENTRIES = TW_TOTAL + 16 * T;
 };
 
 // Twiddles of tree depths 0-3 (even nodes).  They do not depend on M, so they are compile-time constants read through the
@@ -147,18 +160,17 @@ template <bool INV> __device__ __forceinline__ void pass16(cplx (&v)[16], const 
     }
 }
 
-// lane(h=0).v[8+k] <-> lane(h=1).v[k] with the lane at distance `mask`: afterwards every lane owns complete (lo,hi)
-// pairs (v[k], v[8+k]).  An involution: the inverse transform applies it again.
-__device__ __forceinline__ void half_swap(cplx (&v)[16], const int mask, const bool h) {
+// every lane trades its odd registers with the lane at distance `mask` (an involution)
+__device__ __forceinline__ void odd_swap(cplx (&v)[16], const int mask) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const cplx a = v[k], c = v[8 + k];
-        cplx x = h ? a : c;
-        x.x = __shfl_xor_sync(0xffffffffu, x.x, mask);
-        x.y = __shfl_xor_sync(0xffffffffu, x.y, mask);
-        v[k] = h ? x : a;
-        v[8 + k] = h ? c : x;
+    for (int m = 0; m < 8; m++) {
+        v[2 * m + 1].x = __shfl_xor_sync(0xffffffffu, v[2 * m + 1].x, mask);
+        v[2 * m + 1].y = __shfl_xor_sync(0xffffffffu, v[2 * m + 1].y, mask);
     }
+}
+template <int LOGM> __device__ __forceinline__ int tree_side(const int t) {      // side of lane t in the first exchange
+    typedef TreePlan<LOGM> P;
+    return ((t % P::P) >> (P::NS - 1)) & 1;
 }
 
 // Forward: in  v[m] = z_{t + T m}  (t = lane in [0,T), natural coefficient order, stride T)
@@ -181,28 +193,23 @@ __device__ __forceinline__ void tree_forward_a(cplx (&v)[16], cplx* __restrict__
 template <int LOGM>
 __device__ __forceinline__ void tree_forward_b(cplx (&v)[16], const cplx* __restrict__ tw, const int t) {      // depths 4-7
     typedef TreePlan<LOGM> P;
-    pass16<false>(v, tw + P::TB + t / P::P, 16);
+    pass16<false>(v, tw + P::TB + tree_side<LOGM>(t) * 128 + t / P::P, 16);
 }
 template <int LOGM>
 __device__ __forceinline__ void tree_forward_c(cplx (&v)[16], const cplx* __restrict__ tw, const int t) {      // depths 8..
     typedef TreePlan<LOGM> P;
     constexpr int T = P::T;
-    const int p = t % P::P;
     {   // depth 8
-        const bool h = (p >> (P::NS - 1)) & 1;
-        half_swap(v, P::P >> 1, h);
-        const cplx* e = tw + P::TC0 + (t >> (P::NS - 1));
+        odd_swap(v, P::P >> 1);
+        const cplx* e = tw + P::TC0 + t;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const cplx w = e[k * P::G0];
-            bf_fwd(v[2 * k], v[8 + 2 * k], w); bf_fwd_i(v[2 * k + 1], v[8 + 2 * k + 1], w);
-        }
+        for (int m = 0; m < 8; m++) bf_fwd(v[2 * m], v[2 * m + 1], e[m * T]);
     }
     if (P::NS > 1) {   // depth 9 (M = 1024)
-        half_swap(v, 1, p & 1);
+        odd_swap(v, 1);
         const cplx* e = tw + P::TC1 + t;
 #pragma unroll
-        for (int k = 0; k < 8; k++) bf_fwd(v[k], v[8 + k], e[k * T]);
+        for (int m = 0; m < 8; m++) bf_fwd(v[2 * m], v[2 * m + 1], e[m * T]);
     }
 }
 template <int LOGM>
@@ -212,7 +219,7 @@ __device__ __forceinline__ void tree_forward(cplx (&v)[16], cplx* __restrict__ b
     tree_forward_c<LOGM>(v, tw, t);
 }
 
-// Backward: the exact mirror.  in v[i] = spectrum slot i ; out v[m] = M * z_{t + T m}
+// Backward: the exact mirror.  in v[i] = spectrum slot i (times g) ; out v[m] = M * z_{t + T m}
 template <int LOGM>
 __device__ __forceinline__ void tree_backward(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id) {
     typedef TreePlan<LOGM> P;
@@ -221,19 +228,16 @@ __device__ __forceinline__ void tree_backward(cplx (&v)[16], cplx* __restrict__ 
     if (P::NS > 1) {
         const cplx* e = tw + P::TC1 + t;
 #pragma unroll
-        for (int k = 0; k < 8; k++) bf_inv(v[k], v[8 + k], e[k * T]);
-        half_swap(v, 1, p & 1);
+        for (int m = 0; m < 8; m++) bf_inv(v[2 * m], v[2 * m + 1], e[m * T]);
+        odd_swap(v, 1);
     }
     {
-        const cplx* e = tw + P::TC0 + (t >> (P::NS - 1));
+        const cplx* e = tw + P::TC0 + t;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const cplx w = e[k * P::G0];
-            bf_inv(v[2 * k], v[8 + 2 * k], w); bf_inv_i(v[2 * k + 1], v[8 + 2 * k + 1], w);
-        }
-        half_swap(v, P::P >> 1, (p >> (P::NS - 1)) & 1);
+        for (int m = 0; m < 8; m++) bf_inv(v[2 * m], v[2 * m + 1], e[m * T]);
+        odd_swap(v, P::P >> 1);
     }
-    pass16<true>(v, tw + P::TB + b, 16);
+    pass16<true>(v, tw + P::TB + tree_side<LOGM>(t) * 128 + b, 16);
     lanes_sync<T>(bar_id);
 #pragma unroll
     for (int u = 0; u < 16; u++) buf[b * P::S + p + P::P * u] = v[u];

@@ -10,12 +10,13 @@
 // binary128 rounds identically except on astronomically unlikely near-ties.
 #include <quadmath.h>
 #include <stdint.h>
+#include <vector>
 
 namespace tfhe_b200 {
 
 int fft_table_entries(int logM) {
     const int M = 1 << logM, T = M / 16;
-    return 8 + 128 + 4 * 32 + (logM == 10 ? 8 * T : 0);
+    return 8 + 256 + 8 * T + (logM == 10 ? 8 * T : 0) + 16 * T;     // TA | TB | TC0 | TC1 | TG  (TreePlan)
 }
 
 static unsigned bitrev(unsigned x, int bits) {
@@ -29,27 +30,55 @@ static void node(double*& p, int d, unsigned nu) {   // w(d,nu)
     *p++ = (double)sinq(ang);
 }
 
+typedef __complex128 q128;
+static q128 nodeq(int d, unsigned nu) {
+    const __float128 ang = 2 * M_PIq * (__float128)(1 + 4 * (long)bitrev(nu, d)) / (__float128)(1L << (d + 3));
+    return cosq(ang) + sinq(ang) * 1.0Qi;
+}
+static void put(double*& p, q128 z) { *p++ = (double)crealq(z); *p++ = (double)cimagq(z); }
+
+// Layout and the select-free exchange construction: TreePlan in tree_fft.cuh; model: tools/tree_fft_model.py (tables2).
 void make_fft_tables(int logM, double* out) {
-    const int M = 1 << logM, T = M / 16, NS = logM - 8;
+    const int M = 1 << logM, T = M / 16, P = T / 16, NS = logM - 8;
     double* p = out;
     // TA: depths 0-3, even nodes
     node(p, 0, 0); node(p, 1, 0); node(p, 2, 0); node(p, 2, 2);
     for (int s = 0; s < 4; s++) node(p, 3, 2 * s);
-    // TB[e][b]: depths 4-7 below depth-4 node b
-    for (int e = 0; e < 8; e++)
-        for (int b = 0; b < 16; b++) {
-            if (e == 0) node(p, 4, b);
-            else if (e == 1) node(p, 5, 2 * b);
-            else if (e < 4) node(p, 6, 4 * b + 2 * (e - 2));
-            else node(p, 7, 8 * b + 2 * (e - 4));
+    // TB[h][e][b]: depths 4-7 below depth-4 node b; side-1 lanes take depth 7 negated
+    for (int h = 0; h < 2; h++)
+        for (int e = 0; e < 8; e++)
+            for (int b = 0; b < 16; b++) {
+                if (e == 0) node(p, 4, b);
+                else if (e == 1) node(p, 5, 2 * b);
+                else if (e < 4) node(p, 6, 4 * b + 2 * (e - 2));
+                else put(p, (h ? -1 : 1) * nodeq(7, 8 * b + 2 * (e - 4)));
+            }
+    // TC0[m][t], TC1[m][t], TG[i][t]
+    std::vector<q128> c8((size_t)8 * T), c9((size_t)8 * T), g((size_t)16 * T);
+    for (int t = 0; t < T; t++) {
+        const int b = t / P, pp = t % P;
+        const int h8 = (pp >> (NS - 1)) & 1, h9 = NS > 1 ? (pp & 1) : 0;
+        for (int m = 0; m < 8; m++) {
+            const unsigned A = 16 * b + 2 * m + h8;                 // the depth-8 node this lane completes
+            const q128 w8 = nodeq(8, A);
+            q128 c = h8 ? conjq(w8) : w8;
+            if (NS > 1 && h9) c = -c;
+            c8[(size_t)m * T + t] = c;
+            const q128 g8[2] = {h8 ? conjq(w8) : (q128)1, h8 ? -conjq(w8) : (q128)1};     // on (plus, minus) of node A
+            if (NS == 1) {
+                g[(size_t)(2 * m) * T + t] = g8[0]; g[(size_t)(2 * m + 1) * T + t] = g8[1];
+            } else {
+                const unsigned D = 2 * A + h9;                      // depth-9 node: plus (h9 = 0) or minus (h9 = 1) child of A
+                const q128 w9 = nodeq(9, D);
+                c9[(size_t)m * T + t] = h9 ? conjq(w9) : w9;
+                g[(size_t)(2 * m) * T + t] = g8[h9] * (h9 ? conjq(w9) : (q128)1);
+                g[(size_t)(2 * m + 1) * T + t] = g8[h9] * (h9 ? -conjq(w9) : (q128)1);
+            }
         }
-    // TC0[k][g]: depth 8, nodes 8g + 2k
-    for (int k = 0; k < 4; k++)
-        for (int g = 0; g < 32; g++) node(p, 8, 8 * g + 2 * k);
-    // TC1[k][t]: depth 9 (M = 1024), nodes 16(t>>1) + 2k + (t&1)
-    if (NS > 1)
-        for (int k = 0; k < 8; k++)
-            for (int t = 0; t < T; t++) node(p, 9, 16 * (t >> 1) + 2 * k + (t & 1));
+    }
+    for (size_t i = 0; i < c8.size(); i++) put(p, c8[i]);
+    if (NS > 1) for (size_t i = 0; i < c9.size(); i++) put(p, c9[i]);
+    for (size_t i = 0; i < g.size(); i++) put(p, g[i]);
 }
 
 static void fix64(__float128 x, uint64_t* lo, uint64_t* hi) {
