@@ -121,6 +121,7 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
     tree_forward_a<LOGM>(v, buf, tw, t, bar_id);                // ends with a sync: nobody reads buf any more
     if (!ALLREG && t == 0) s0.request(bkp, POLY);
     tree_forward_b<LOGM>(v, tw, t);
+    TL(4);
     // BK[p][1] goes to registers: requested after depths 4-7 (v + 16 key values + that pass's temporaries do not fit in 168
     // registers), its L2 round trip hides behind the shuffle stage and the first multiply-accumulate
     const cplx* __restrict__ g1 = bkp + P::M + t;
@@ -133,9 +134,14 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
         cplx b0r[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) b0r[i] = __ldg(g1 - P::M + i * P::T);
+        TL(5);
         tree_forward_c<LOGM>(v, tw, t);
+        TL(6);
+        // (a software-pipelined variant, next chunk's tcgen05.ld in flight during the FMAs, was 5 % slower: profiles/r1_notes.md)
         mac_tmem<FIRST>(tacc, v, [&](int i) { return b0r[i]; });
+        TL(7);
         mac_tmem<FIRST>(tacc + 64, v, [&](int i) { return b1[i]; });
+        TL(8);
     } else {
         tree_forward_c<LOGM>(v, tw, t);
         s0.wait();
@@ -169,6 +175,7 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
         const Torus* __restrict__ aq = acc + q * N;
         const int sh = W - (lev + 1) * Bgbit;
         cplx v[16];
+        TL(0);
         if (STASH && lev > 0) {
             uint32_t w[4][WPC];
 #pragma unroll
@@ -214,13 +221,16 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
             }
             if (stash) tmem_wait_st();
         }
+        TL(1);
         if (p == 0) forward_and_mac<LOGM, true, ALLREG>(v, tacc, bk, buf, s0, tw, t, bar_id);
         else        forward_and_mac<LOGM, false, ALLREG>(v, tacc, bk + (size_t)(p * 2) * M, buf, s0, tw, t, bar_id);
     }
     // every lane has finished reading the accumulator once it passes the first sync inside tree_backward
     {
         cplx R[16];
+        TL(0);
         load_tmem(R, tacc);
+        TL(9);
         tree_backward<LOGM>(R, buf, tw, t, bar_id);
 #pragma unroll
         for (int m = 0; m < 16; m++) {
@@ -228,10 +238,12 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
             acc[j] = (Torus)((U)acc[j] + (U)to_torus(R[m].x, (Torus)0));
             acc[j + M] = (Torus)((U)acc[j + M] + (U)to_torus(R[m].y, (Torus)0));
         }
+        TL(14);
     }
     {
         cplx R[16];
         load_tmem(R, tacc + 64);
+        TL(9);
         tree_backward<LOGM>(R, buf, tw, t, bar_id);
 #pragma unroll
         for (int m = 0; m < 16; m++) {
@@ -239,8 +251,10 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
             acc[N + j] = (Torus)((U)acc[N + j] + (U)to_torus(R[m].x, (Torus)0));
             acc[N + j + M] = (Torus)((U)acc[N + j + M] + (U)to_torus(R[m].y, (Torus)0));
         }
+        TL(14);
     }
     lanes_sync<T>(bar_id);      // accumulator writes visible before the next step's rotated reads
+    TL(15);
 }
 
 template <int LOGM, typename Torus, int GROUPS> struct BRSmem {
@@ -337,6 +351,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
             }
         }
         lanes_sync<T>(bar_id);
+        TL(-1);
 
         // ---- n CMUX steps (tfhe_blindRotate_FFT :348-354); a step with bara == 0 is skipped like the reference does (:350).
         // The next rotation amount is fetched one step ahead.
@@ -349,6 +364,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
             cmux_step<LOGM, Torus, STASH, ALLREG>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, s0, tw, t, bar_id);
         }
 
+        TL(99);
         // ---- epilogue
         if (A.mode == BR_ACCUM) {
             Torus* dst = reinterpret_cast<Torus*>(A.accum) + (size_t)ct * 2 * N;
@@ -369,6 +385,13 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
+#ifdef BR_TIMELINE
+}  // namespace tfhe_b200
+extern "C" __attribute__((visibility("default"))) int tfhe_b200_dev_timeline(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, tfhe_b200::g_tl_acc, sizeof(long long) * 32 * 32);
+}
+namespace tfhe_b200 {
+#endif
 static bool g_inited = false;
 // Configurations (profiles/r1_notes.md has the sweep): 8 warps per SM with every key value prefetched into registers is the
 // fastest (166 k bootstraps/s); 12 warps with BK[p][0] landing in shared memory by TMA is kept for comparison (146 k/s).

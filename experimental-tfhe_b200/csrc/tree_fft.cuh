@@ -114,6 +114,27 @@ __device__ __constant__ double c_tree_ta[16] = {
     0x1.294062ed59f06p-2, 0x1.e9f4156c62ddap-1,   // w(3,6)
 };
 
+// Development instrumentation (tools/br_timeline.py builds a private library with -DBR_TIMELINE): per-warp cycle counts
+// between marks, accumulated by lane 0.  Compiles to nothing in the product build.
+#ifdef BR_TIMELINE
+__device__ long long g_tl_acc[32 * 32];
+__device__ __forceinline__ void tl_mark(const int k) {
+    __shared__ long long tl_last[32];
+    __shared__ long long tl_sum[32][32];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        const long long now = clock64();
+        if (k < 0) { for (int i = 0; i < 32; i++) tl_sum[w][i] = 0; }
+        else if (k == 99) { if (blockIdx.x == 0) for (int i = 0; i < 32; i++) g_tl_acc[w * 32 + i] = tl_sum[w][i]; }
+        else tl_sum[w][k] += now - tl_last[w];
+        tl_last[w] = clock64();
+    }
+}
+#define TL(k) tl_mark(k)
+#else
+#define TL(k) do {} while (0)
+#endif
+
 template <int T> __device__ __forceinline__ void lanes_sync(int bar_id) {
     if (T == 32) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
@@ -181,6 +202,7 @@ __device__ __forceinline__ void tree_forward_a(cplx (&v)[16], cplx* __restrict__
     typedef TreePlan<LOGM> P;
     constexpr int T = P::T;
     pass16<false>(v, reinterpret_cast<const cplx*>(c_tree_ta), 1);
+    TL(2);
     lanes_sync<T>(bar_id);                                   // WAR: earlier reads of buf
 #pragma unroll
     for (int m = 0; m < 16; m++) buf[m * P::S + t] = v[m];
@@ -189,6 +211,7 @@ __device__ __forceinline__ void tree_forward_a(cplx (&v)[16], cplx* __restrict__
 #pragma unroll
     for (int u = 0; u < 16; u++) v[u] = buf[b * P::S + p + P::P * u];
     lanes_sync<T>(bar_id);                                   // every lane is done with buf
+    TL(3);
 }
 template <int LOGM>
 __device__ __forceinline__ void tree_forward_b(cplx (&v)[16], const cplx* __restrict__ tw, const int t) {      // depths 4-7
@@ -237,14 +260,18 @@ __device__ __forceinline__ void tree_backward(cplx (&v)[16], cplx* __restrict__ 
         for (int m = 0; m < 8; m++) bf_inv(v[2 * m], v[2 * m + 1], e[m * T]);
         odd_swap(v, P::P >> 1);
     }
+    TL(10);
     pass16<true>(v, tw + P::TB + tree_side<LOGM>(t) * 128 + b, 16);
+    TL(11);
     lanes_sync<T>(bar_id);
 #pragma unroll
     for (int u = 0; u < 16; u++) buf[b * P::S + p + P::P * u] = v[u];
     lanes_sync<T>(bar_id);
 #pragma unroll
     for (int m = 0; m < 16; m++) v[m] = buf[m * P::S + t];
+    TL(12);
     pass16<true>(v, reinterpret_cast<const cplx*>(c_tree_ta), 1);
+    TL(13);
 }
 
 // ---------------------------------------------------------------------------------------------
