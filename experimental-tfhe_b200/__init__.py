@@ -17,7 +17,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtfhe_b200.so")
+LIB_PATH = os.environ.get("TFHE_B200_LIB") or os.path.join(_HERE, "libtfhe_b200.so")   # override: development builds only
 
 OK = 0
 GATES = {"NAND": 0, "AND": 1, "OR": 2, "NOR": 3, "XOR": 4, "XNOR": 5, "ANDNY": 6, "ANDYN": 7, "ORNY": 8, "ORYN": 9}

@@ -97,6 +97,27 @@ __device__ __forceinline__ void mac_tmem(const uint32_t taddr, const cplx (&v)[1
     }
     tmem_wait_st();
 }
+// same, key values from tensor memory (KeyPipe): kaddr = the 64 key columns of this polynomial
+template <bool FIRST>
+__device__ __forceinline__ void mac_tmem_keytm(const uint32_t taddr, const uint32_t kaddr, const cplx (&v)[16]) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        uint32_t r[16], kq[16];
+        TFHE_TLD16(kq, kaddr + 16 * c);
+        if (!FIRST) { TFHE_TLD16(r, taddr + 16 * c); }
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            cplx R = FIRST ? make_double2(0.0, 0.0)
+                           : make_double2(__hiloint2double((int)r[4 * i + 1], (int)r[4 * i]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]));
+            const cplx b = make_double2(__hiloint2double((int)kq[4 * i + 1], (int)kq[4 * i]), __hiloint2double((int)kq[4 * i + 3], (int)kq[4 * i + 2]));
+            cfma(R, v[4 * c + i], b);
+            r[4 * i] = (uint32_t)__double2loint(R.x); r[4 * i + 1] = (uint32_t)__double2hiint(R.x);
+            r[4 * i + 2] = (uint32_t)__double2loint(R.y); r[4 * i + 3] = (uint32_t)__double2hiint(R.y);
+        }
+        TFHE_TST16(r, taddr + 16 * c);
+    }
+}
 __device__ __forceinline__ void load_tmem(cplx (&R)[16], const uint32_t taddr) {
 #pragma unroll
     for (int c = 0; c < 4; c++) {
@@ -109,29 +130,25 @@ __device__ __forceinline__ void load_tmem(cplx (&R)[16], const uint32_t taddr) {
     }
 }
 
-// forward transform of one digit polynomial + its two multiply-accumulates.  Key polynomial BK[p][0] lands in the transpose
-// buffer by TMA as soon as the transpose is over (bk_pipe.cuh); BK[p][1] is prefetched into registers (the accumulators no
-// longer occupy them) while the second half of the transform runs.
+// forward transform of one digit polynomial + its two multiply-accumulates.
+//   ALLREG : both key polynomials are prefetched into registers with ld.global.nc right after depths 4-7 (8 warps per SM)
+//   else   : they wait in tensor memory (KeyPipe, bk_pipe.cuh), no key registers at all (12 warps per SM)
 template <int LOGM, bool FIRST, bool ALLREG>
 __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t tacc, const cplx* __restrict__ bkp,
-                                                cplx* __restrict__ buf, BkSlot& s0,
+                                                cplx* __restrict__ buf, KeyPipe& kp,
                                                 const cplx* __restrict__ tw, const int t, const int bar_id) {
     typedef TreePlan<LOGM> P;
-    constexpr uint32_t POLY = P::M * sizeof(cplx);
-    tree_forward_a<LOGM>(v, buf, tw, t, bar_id);                // ends with a sync: nobody reads buf any more
-    if (!ALLREG && t == 0) s0.request(bkp, POLY);
+    tree_forward_a<LOGM>(v, buf, tw, t, bar_id);
+    if (!ALLREG && (t & 31) == 0) kp.poll();
     tree_forward_b<LOGM>(v, tw, t);
     TL(4);
-    // BK[p][1] goes to registers: requested after depths 4-7 (v + 16 key values + that pass's temporaries do not fit in 168
-    // registers), its L2 round trip hides behind the shuffle stage and the first multiply-accumulate
-    const cplx* __restrict__ g1 = bkp + P::M + t;
-    asm volatile("" : "+l"(g1) : "d"(v[0].x), "d"(v[15].y));          // do not hoist the loads above the pass
-    cplx b1[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) b1[i] = __ldg(g1 + i * P::T);
     if (ALLREG) {
-        // 8-warp configuration: enough registers to take BK[p][0] the same way (no shared-memory traffic for the key at all)
-        cplx b0r[16];
+        // its L2 round trip hides behind the exchange stage
+        const cplx* __restrict__ g1 = bkp + P::M + t;
+        asm volatile("" : "+l"(g1) : "d"(v[0].x), "d"(v[15].y));          // do not hoist the loads above the pass
+        cplx b1[16], b0r[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) b1[i] = __ldg(g1 + i * P::T);
 #pragma unroll
         for (int i = 0; i < 16; i++) b0r[i] = __ldg(g1 - P::M + i * P::T);
         TL(5);
@@ -144,10 +161,17 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
         TL(8);
     } else {
         tree_forward_c<LOGM>(v, tw, t);
-        s0.wait();
-        const cplx* b0 = reinterpret_cast<const cplx*>(s0.dst) + t;
-        mac_tmem<FIRST>(tacc, v, [&](int i) { return b0[i * P::T]; });
-        mac_tmem<FIRST>(tacc + 64, v, [&](int i) { return b1[i]; });
+        TL(6);
+        kp.acquire(t & 31);
+        TL(16);
+        mac_tmem_keytm<FIRST>(tacc, kp.tkey, v);
+        TL(7);
+        mac_tmem_keytm<FIRST>(tacc + 64, kp.tkey + 64, v);
+        TL(8);
+        kp.release(t & 31);              // the key loads of both polynomials have been waited for
+        TL(17);
+        tmem_wait_st();
+        TL(18);
     }
 }
 
@@ -159,7 +183,7 @@ template <typename Torus> struct StashWords { static constexpr int PER_C = 8 * (
 template <int LOGM, typename Torus, bool STASH, bool ALLREG>
 __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, const cplx* __restrict__ bk,
                                           const int l, const int Bgbit, cplx* __restrict__ buf, const uint32_t tacc,
-                                          BkSlot& s0, const cplx* __restrict__ tw, const int t, const int bar_id) {
+                                          KeyPipe& kp, const cplx* __restrict__ tw, const int t, const int bar_id) {
     typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
     constexpr int M = P::M, N = P::N, T = P::T, W = TorusTraits<Torus>::W;
@@ -176,6 +200,7 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
         const int sh = W - (lev + 1) * Bgbit;
         cplx v[16];
         TL(0);
+        if (!ALLREG && (t & 31) == 0) kp.poll();                 // keep the key stream moving (bk_pipe.cuh)
         if (STASH && lev > 0) {
             uint32_t w[4][WPC];
 #pragma unroll
@@ -222,8 +247,8 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
             if (stash) tmem_wait_st();
         }
         TL(1);
-        if (p == 0) forward_and_mac<LOGM, true, ALLREG>(v, tacc, bk, buf, s0, tw, t, bar_id);
-        else        forward_and_mac<LOGM, false, ALLREG>(v, tacc, bk + (size_t)(p * 2) * M, buf, s0, tw, t, bar_id);
+        if (p == 0) forward_and_mac<LOGM, true, ALLREG>(v, tacc, bk, buf, kp, tw, t, bar_id);
+        else        forward_and_mac<LOGM, false, ALLREG>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp, tw, t, bar_id);
     }
     // every lane has finished reading the accumulator once it passes the first sync inside tree_backward
     {
@@ -257,19 +282,26 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
     TL(15);
 }
 
-template <int LOGM, typename Torus, int GROUPS> struct BRSmem {
+// Shared memory: twiddles | CTA control (KeyPipeShared, TMEM base) | key staging (KeyPipe only) | per group: transpose buffer, ACC
+// Tensor memory : per warp R0 (64 columns) | R1 (64) | stash (STASH only), warps of a lane quarter side by side; the key columns
+//                 of the KeyPipe configuration come after the last warp's window.
+template <int LOGM, typename Torus, int GROUPS, bool STASH, bool ALLREG> struct BRSmem {
     typedef TreePlan<LOGM> P;
     static constexpr size_t TW_BYTES = sizeof(cplx) * ((P::TW_TOTAL + 7) & ~7);        // 128-byte multiple
-    static constexpr size_t CTRL_BYTES = 128;                                          // mbarrier (+ TMEM base in group 0)
-    static constexpr size_t BUF_BYTES = (sizeof(cplx) * P::BUF + 127) & ~(size_t)127;  // transpose buffer, also lands BK[p][0]
+    static constexpr size_t CTRL_BYTES = 128;
+    static constexpr size_t CHUNK_BYTES = sizeof(cplx) * 2 * P::M;                      // BK_i[p][0..1]
+    static constexpr size_t STAGE_BYTES = ALLREG ? 0 : CHUNK_BYTES;
+    static constexpr size_t BUF_BYTES = (sizeof(cplx) * P::BUF + 127) & ~(size_t)127;  // transpose buffer
     static constexpr size_t ACC_BYTES = sizeof(Torus) * 2 * P::N;
-    static constexpr size_t GROUP_BYTES = CTRL_BYTES + BUF_BYTES + ACC_BYTES;
-    static constexpr size_t TOTAL = TW_BYTES + GROUPS * GROUP_BYTES;
+    static constexpr size_t GROUP_BYTES = BUF_BYTES + ACC_BYTES;
+    static constexpr size_t GROUPS_OFF = TW_BYTES + CTRL_BYTES + STAGE_BYTES;
+    static constexpr size_t TOTAL = GROUPS_OFF + GROUPS * GROUP_BYTES;
     static constexpr int WARPS = GROUPS * P::T / 32;
-    static_assert(sizeof(cplx) * P::BUF >= sizeof(cplx) * P::M, "transpose buffer must hold one key polynomial");
     static_assert(TOTAL <= 232448, "shared memory budget (227 KB) exceeded");
-    static constexpr int TMEM_COLS = 128 + 4 * StashWords<Torus>::PER_C;               // R0 (64) | R1 (64) | stash of u (32 words)
-    static_assert((WARPS + 3) / 4 * TMEM_COLS <= 512, "tensor memory: TMEM_COLS columns per warp, 4 lane quarters");
+    static constexpr int TMEM_COLS = 128 + (STASH ? 4 * StashWords<Torus>::PER_C : 0);
+    static constexpr int KEY_COL = (WARPS + 3) / 4 * TMEM_COLS;
+    static_assert(KEY_COL + (ALLREG ? 0 : 128) <= 512, "tensor memory columns exceeded");
+    static_assert(ALLREG || P::T == 32, "KeyPipe: one warp per accumulator");
 };
 
 // rotation amount i of sample ct (i == n: the b part), straight from the kernel's inputs -- nothing is staged in shared memory
@@ -295,20 +327,31 @@ template <int LOGM, typename Torus, int GROUPS, bool STASH, bool ALLREG>
 __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_kernel(const BRArgs A) {
     typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
-    typedef BRSmem<LOGM, Torus, GROUPS> S;
+    typedef BRSmem<LOGM, Torus, GROUPS, STASH, ALLREG> S;
     constexpr int M = P::M, N = P::N, T = P::T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* tw = reinterpret_cast<cplx*>(smem_raw);
     const int g = threadIdx.x / T, t = threadIdx.x % T, warp = threadIdx.x >> 5;
     const int bar_id = 1 + g;
-    unsigned char* gbase = smem_raw + S::TW_BYTES + (size_t)g * S::GROUP_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(gbase);
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(smem_raw + S::TW_BYTES + 64);     // in group 0's control block
-    cplx* buf = reinterpret_cast<cplx*>(gbase + S::CTRL_BYTES);
-    Torus* acc = reinterpret_cast<Torus*>(gbase + S::CTRL_BYTES + S::BUF_BYTES);
+    KeyPipeShared* kps = reinterpret_cast<KeyPipeShared*>(smem_raw + S::TW_BYTES);
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(smem_raw + S::TW_BYTES + 64);
+    unsigned char* gbase = smem_raw + S::GROUPS_OFF + (size_t)g * S::GROUP_BYTES;
+    cplx* buf = reinterpret_cast<cplx*>(gbase);
+    Torus* acc = reinterpret_cast<Torus*>(gbase + S::BUF_BYTES);
+
+    // unit = (sample, test-vector index); n_mu > 1 only on the circuit-bootstrap path
+    const int n_mu = A.n_mu > 0 ? A.n_mu : 1;
+    const long total_units = (long)A.count * n_mu;
+    const long unit = (long)blockIdx.x * GROUPS + g;
 
     for (int i = threadIdx.x; i < P::TW_TOTAL; i += GROUPS * T) tw[i] = A.tw[i];
-    if (t == 0) { mbar_init(&bars[0], 1); mbar_fence_init(); }
+    if (threadIdx.x == 0) {
+        const long left = total_units - (long)blockIdx.x * GROUPS;
+        mbar_init(&kps->tma_bar, 1); mbar_init(&kps->full_bar, 1);
+        kps->done = 0; kps->tma_next = 1; kps->copy_next = 1;
+        kps->active = (uint32_t)(left < GROUPS ? left : GROUPS) * (T / 32);
+        mbar_fence_init();
+    }
     if (warp == 0) {     // the whole SM's tensor memory: one CTA per SM (shared-memory bound), nobody else wants it
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_base_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -318,11 +361,11 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_base_slot;
     const uint32_t tacc = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)S::TMEM_COLS;   // R0 | R1 | stash
-    BkSlot s0{&bars[0], reinterpret_cast<unsigned char*>(buf), 0u};
+    KeyPipe kp{kps, smem_raw + S::TW_BYTES + S::CTRL_BYTES, reinterpret_cast<const unsigned char*>(A.bkfft),
+               tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)S::KEY_COL, tmem_base + (uint32_t)S::KEY_COL,
+               (uint32_t)S::CHUNK_BYTES, (uint32_t)(A.n * 2 * A.l), 0u};
+    if (!ALLREG && threadIdx.x == 0) kp.prologue();
 
-    // unit = (sample, test-vector index); n_mu > 1 only on the circuit-bootstrap path
-    const int n_mu = A.n_mu > 0 ? A.n_mu : 1;
-    const long unit = (long)blockIdx.x * GROUPS + g;
     if (unit < (long)A.count * n_mu) {                 // idle groups of the last CTA fall through to the final barrier
         const int ct = (int)(unit / n_mu), w = (int)(unit % n_mu);
         const int n = A.n;
@@ -360,8 +403,11 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
         for (int i = 0; i < n; i++) {
             const int a = a_next;
             if (i + 1 < n) a_next = fetch_bara<LOGM, Torus>(A, ct, i + 1);
-            if (a == 0) continue;
-            cmux_step<LOGM, Torus, STASH, ALLREG>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, s0, tw, t, bar_id);
+            if (a == 0) {
+                if (!ALLREG) for (int p = 0; p < 2 * l; p++) { kp.acquire(t & 31); kp.release(t & 31); }     // stay aligned with the key stream
+                continue;
+            }
+            cmux_step<LOGM, Torus, STASH, ALLREG>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, kp, tw, t, bar_id);
         }
 
         TL(99);
@@ -393,19 +439,27 @@ extern "C" __attribute__((visibility("default"))) int tfhe_b200_dev_timeline(lon
 namespace tfhe_b200 {
 #endif
 static bool g_inited = false;
-// Configurations (profiles/r1_notes.md has the sweep): 8 warps per SM with every key value prefetched into registers is the
-// fastest (166 k bootstraps/s); 12 warps with BK[p][0] landing in shared memory by TMA is kept for comparison (146 k/s).
-constexpr int G32 = 8, G32_TMA = 12, G64 = 4;     // accumulators per CTA (N=1024: one warp each; N=2048: two warps each)
+// Configurations (profiles/r1_notes.md has the sweep):
+//   default:  8 warps per SM, key prefetched into registers, stash                    <9, int32,  8, true,  true>   172 k/s
+//   keytm  : 12 warps per SM, key through tensor memory (KeyPipe), no stash           <9, int32, 12, false, false>  163 k/s
+//            (free-running 12 warps with the key "already there" measured 201 k/s; the CTA-wide lockstep on the single
+//             tensor-memory key buffer and the 2 200-cycle copy issue per chunk give that back -- kept selectable for round 2)
+constexpr int G32 = 8, G32_KP = 12, G64 = 4;     // accumulators per CTA (N=1024: one warp each; N=2048: two warps each)
 
 template <int LOGM, typename Torus, int GROUPS, bool STASH, bool ALLREG> static cudaError_t br_attr() {
     return cudaFuncSetAttribute(blind_rotate_kernel<LOGM, Torus, GROUPS, STASH, ALLREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)BRSmem<LOGM, Torus, GROUPS>::TOTAL);
+                                (int)BRSmem<LOGM, Torus, GROUPS, STASH, ALLREG>::TOTAL);
+}
+template <int LOGM, typename Torus, int GROUPS, bool STASH, bool ALLREG> static cudaError_t br_launch(const BRArgs& a, long units, cudaStream_t s) {
+    const int grid = (int)((units + GROUPS - 1) / GROUPS);
+    blind_rotate_kernel<LOGM, Torus, GROUPS, STASH, ALLREG><<<grid, GROUPS * TreePlan<LOGM>::T, BRSmem<LOGM, Torus, GROUPS, STASH, ALLREG>::TOTAL, s>>>(a);
+    return cudaGetLastError();
 }
 cudaError_t blind_rotate_init() {
     cudaError_t e;
+    if ((e = br_attr<9, int32_t, G32_KP, false, false>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32, true, true>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32, false, true>()) != cudaSuccess) return e;
-    if ((e = br_attr<9, int32_t, G32_TMA, true, false>()) != cudaSuccess) return e;
     if ((e = br_attr<10, int64_t, G64, false, true>()) != cudaSuccess) return e;
     g_inited = true;
     return cudaSuccess;
@@ -414,29 +468,19 @@ cudaError_t blind_rotate_init() {
 cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
     if (!g_inited) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
     if (a.count <= 0) return cudaSuccess;
-    // development knob: TFHE_B200_BR_VARIANT = nostash | tma selects the measured alternatives
+    // development knob: TFHE_B200_BR_VARIANT = keytm | nostash selects the measured alternatives
     static const char* variant = getenv("TFHE_B200_BR_VARIANT");
-    if (variant && variant[0] == 't') {
-        const int grid = (a.count + G32_TMA - 1) / G32_TMA;
-        blind_rotate_kernel<9, int32_t, G32_TMA, true, false><<<grid, G32_TMA * TreePlan<9>::T, BRSmem<9, int32_t, G32_TMA>::TOTAL, s>>>(a);
-    } else if (variant && variant[0] == 'n') {
-        const int grid = (a.count + G32 - 1) / G32;
-        blind_rotate_kernel<9, int32_t, G32, false, true><<<grid, G32 * TreePlan<9>::T, BRSmem<9, int32_t, G32>::TOTAL, s>>>(a);
-    } else {
-        const int grid = (a.count + G32 - 1) / G32;
-        blind_rotate_kernel<9, int32_t, G32, true, true><<<grid, G32 * TreePlan<9>::T, BRSmem<9, int32_t, G32>::TOTAL, s>>>(a);
-    }
-    return cudaGetLastError();
+    if (variant && variant[0] == 'k') return br_launch<9, int32_t, G32_KP, false, false>(a, a.count, s);
+    if (variant && variant[0] == 'n') return br_launch<9, int32_t, G32, false, true>(a, a.count, s);
+    return br_launch<9, int32_t, G32, true, true>(a, a.count, s);
 }
 cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
     if (!g_inited) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
     if (a.count <= 0) return cudaSuccess;
     const long units = (long)a.count * (a.n_mu > 0 ? a.n_mu : 1);
-    const int grid = (int)((units + G64 - 1) / G64);
     // no stash for Torus64: 64 columns of u per lane cost more tensor-memory traffic than the re-reads save (232 vs 225 ms
     // per 4096 circuit bootstraps, profiles/r1_notes.md)
-    blind_rotate_kernel<10, int64_t, G64, false, true><<<grid, G64 * TreePlan<10>::T, BRSmem<10, int64_t, G64>::TOTAL, s>>>(a);
-    return cudaGetLastError();
+    return br_launch<10, int64_t, G64, false, true>(a, units, s);
 }
 
 // ---------------------------------------------------------------------------------------------

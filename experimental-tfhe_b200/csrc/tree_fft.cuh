@@ -119,13 +119,13 @@ __device__ __constant__ double c_tree_ta[16] = {
 #ifdef BR_TIMELINE
 __device__ long long g_tl_acc[32 * 32];
 __device__ __forceinline__ void tl_mark(const int k) {
-    __shared__ long long tl_last[32];
-    __shared__ long long tl_sum[32][32];
+    __shared__ long long tl_last[16];
+    __shared__ long long tl_sum[16][20];
     const int w = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
         const long long now = clock64();
-        if (k < 0) { for (int i = 0; i < 32; i++) tl_sum[w][i] = 0; }
-        else if (k == 99) { if (blockIdx.x == 0) for (int i = 0; i < 32; i++) g_tl_acc[w * 32 + i] = tl_sum[w][i]; }
+        if (k < 0) { for (int i = 0; i < 20; i++) tl_sum[w][i] = 0; }
+        else if (k == 99) { if (blockIdx.x == 0) for (int i = 0; i < 20; i++) g_tl_acc[w * 32 + i] = tl_sum[w][i]; }
         else tl_sum[w][k] += now - tl_last[w];
         tl_last[w] = clock64();
     }

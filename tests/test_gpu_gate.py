@@ -225,3 +225,33 @@ def test_full_batch_65536_nand_decrypts(gate_engine, gate_oracle):
     assert np.array_equal((phase > 0).astype(np.int64), 1 - (a & b))
     err = phase - np.where((1 - (a & b)) == 1, g.MU, -g.MU)
     assert np.abs(err).max() < 2**28          # 1/16 of the torus: far from the decision boundary
+
+
+def test_keytm_variant_gates_decrypt():
+    """The tensor-memory key pipeline variant (TFHE_B200_BR_VARIANT=keytm: TMA -> shared staging -> tcgen05.cp -> TMEM, 12 warps in
+    lockstep on the key stream) computes the same gates; a batch that is not a multiple of the CTA size exercises idle groups."""
+    import os, subprocess, sys
+    code = r'''
+import importlib, os, sys
+import numpy as np, torch
+root = sys.argv[1]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+import oracle_lib as O
+mod = importlib.import_module("experimental-tfhe_b200")
+eng = mod.Engine(0)
+g = O.GateOracle(42)
+eng.load_gate_keys(g.engine_params(), g.bk, g.ks)
+B = 1001
+rng = np.random.default_rng(5)
+a = rng.integers(0, 2, size=B); b = rng.integers(0, 2, size=B)
+ca, cb = g.encrypt_bits(a, 11), g.encrypt_bits(b, 12)
+out = torch.empty((B, g.n + 1), dtype=torch.int32, device="cuda")
+eng.bootsGate("NAND", out, torch.from_numpy(ca).cuda(), torch.from_numpy(cb).cuda(), B)
+torch.cuda.synchronize()
+assert np.array_equal(np.asarray(g.decrypt_bits(out.cpu().numpy())).astype(int), 1 - (a & b)), "keytm variant: wrong gate outputs"
+print("OK")
+'''
+    env = dict(os.environ, TFHE_B200_BR_VARIANT="keytm")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code, root], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr

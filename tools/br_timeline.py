@@ -14,7 +14,7 @@ mod.LIB_PATH = os.path.join(ROOT, "experimental-tfhe_b200", "build", "lib_timeli
 eng = mod.Engine(0)
 g = O.GateOracle(42)
 eng.load_gate_keys(g.engine_params(), g.bk, g.ks)
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 8 * 4
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 24 * 2
 ca = torch.randint(-2**31, 2**31 - 1, (B, g.n + 1), dtype=torch.int64, device="cuda").to(torch.int32)
 u = torch.empty((B, g.N + 1), dtype=torch.int32, device="cuda")
 for _ in range(2):
@@ -26,10 +26,11 @@ assert lib.tfhe_b200_dev_timeline(buf) == 0
 a = np.array(buf[:], dtype=np.int64).reshape(32, 32)
 names = {0: "loop/other", 1: "decompose / stash load", 2: "fwd pass A (depths 0-3)", 3: "fwd transpose", 4: "fwd pass B (depths 4-7)", 5: "key LDG issue",
          6: "fwd exchange + depth 8", 7: "MAC q=0", 8: "MAC q=1", 9: "load spectral acc (TMEM)", 10: "inv depth 8 + exchange", 11: "inv pass B",
-         12: "inv transpose", 13: "inv pass A", 14: "torus convert + ACC update", 15: "final sync"}
+         12: "inv transpose", 13: "inv pass A", 14: "torus convert + ACC update", 15: "final sync", 16: "KeyPipe acquire (wait full)", 17: "KeyPipe release (+ copy issue by last warp)", 18: "wait::st"}
 ncmux = 500.0 * 1     # nonzero bara almost always; one bootstrap per warp in the last launch
-w = a[:8].mean(axis=0) / ncmux
+nw = int(os.environ.get("TL_WARPS", "12"))
+w = a[:nw].mean(axis=0) / ncmux
 tot = w.sum()
-print(f"cycles per CMUX per warp (mean of 8 warps of CTA 0): {tot:.0f}")
-for k in range(16):
+print(f"cycles per CMUX per warp (mean over the warps of CTA 0): {tot:.0f}")
+for k in range(19):
     print(f"  {k:2d} {names[k]:32s} {w[k]:8.0f}  {w[k] / tot * 100:5.1f}%")
