@@ -106,12 +106,12 @@ def _centered(x):
 
 def test_bootstrap_woKS_phase(gate_engine, gate_oracle):
     """tfhe_bootstrap_woKS_FFT: extracted LWE(N) sample has phase +-mu; measured output noise variance matches the oracle's
-    (within +-25% at >= 4096 samples; here 1024 GPU vs 256 oracle samples, so +-40%) and the prediction of
+    (within +-25% over >= 4096 samples on both sides) and the prediction of
     the worst-case bound of misc/params-gb.html:94-105 (bk term n*2l*N*(Bg/2)^2*sigma_bk^2 = 2^-15.1 for these keys;
     the oracle measures 2^-16.0)."""
     g = gate_oracle
     rng = np.random.default_rng(21)
-    B = 1024
+    B = 4096
     bits = rng.integers(0, 2, size=B)
     x = g.encrypt_bits(bits, seed=43)
     out = torch.empty((B, g.N + 1), dtype=torch.int32, device=DEV)
@@ -120,11 +120,11 @@ def test_bootstrap_woKS_phase(gate_engine, gate_oracle):
     ph = g.phase_N(out.cpu().numpy())
     expect = np.where(bits == 1, g.MU, -g.MU)
     err_gpu = _centered(ph - expect.astype(np.int32))
-    ref = g.bootstrap_woKS(g.MU, x[:256])
-    err_ref = _centered(g.phase_N(ref) - expect[:256].astype(np.int32))
+    ref = g.bootstrap_woKS(g.MU, x)
+    err_ref = _centered(g.phase_N(ref) - expect.astype(np.int32))
     assert np.abs(err_gpu).max() < 2**28, "phase error beyond 1/16 of the torus: the bit would not decode"
     v_gpu, v_ref = float(np.mean(err_gpu.astype(np.float64)**2)), float(np.mean(err_ref.astype(np.float64)**2))
-    assert 0.6 < v_gpu / v_ref < 1.6, f"noise variance: GPU 2^{np.log2(v_gpu) - 64:.2f} vs oracle 2^{np.log2(v_ref) - 64:.2f}"
+    assert 0.75 < v_gpu / v_ref < 1.25, f"noise variance: GPU 2^{np.log2(v_gpu) - 64:.2f} vs oracle 2^{np.log2(v_ref) - 64:.2f}"
     bound = g.n * 2 * g.l * g.N * (2.0**(g.Bgbit - 1))**2 * g.params.bk_stdev**2 * 2.0**64      # worst-case style bound
     assert 1.0 / 8 < v_gpu / bound < 1.0, f"noise variance 2^{np.log2(v_gpu) - 64:.2f} vs bound 2^{np.log2(bound) - 64:.2f}"
 
