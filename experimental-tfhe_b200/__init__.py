@@ -20,6 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TFHE_B200_LIB") or os.path.join(_HERE, "libtfhe_b200.so")   # override: development builds only
 
 OK = 0
+OP_NOT, OP_COPY, OP_MUX = 16, 17, 18
 GATES = {"NAND": 0, "AND": 1, "OR": 2, "NOR": 3, "XOR": 4, "XNOR": 5, "ANDNY": 6, "ANDYN": 7, "ORNY": 8, "ORYN": 9}
 
 
@@ -68,6 +69,7 @@ _SIGS = {
     "tfhe_b200_bootsGate_batch": [_P, _I, _P, _P, _P, _I, _P],
     "tfhe_b200_bootsNOT_batch": [_P, _P, _P, _I, _P],
     "tfhe_b200_bootsMUX_batch": [_P, _P, _P, _P, _P, _I, _P],
+    "tfhe_b200_circuit_eval_batch": [_P, _P, _I, _P, _I, _I, _P],
     "tfhe_b200_bootsGate_batch_host": [_P, _I, _P, _P, _P, _I],
     "tfhe_b200_IntPolynomial_ifft_batch": [_P, _P, _P, _I, _I, _P],
     "tfhe_b200_TorusPolynomial64_ifft_batch": [_P, _P, _P, _I, _I, _P],
@@ -239,6 +241,12 @@ class Engine:
 
     def bootsMUX(self, result, a, b, c, count, stream=None):
         self._ck(self.lib.tfhe_b200_bootsMUX_batch(self.h, _ptr(result), _ptr(a), _ptr(b), _ptr(c), count, self._stream(stream)), "bootsMUX")
+
+    def circuit_eval(self, gates, wires, n_wires, count, stream=None):
+        """gates: int32 array [n_gates][5] = (op, out, in0, in1, in2) (tfhe_b200_gate); wires: device tensor [n_wires][count][n+1]."""
+        import numpy as np
+        g = np.ascontiguousarray(gates, dtype=np.int32).reshape(-1, 5)
+        self._ck(self.lib.tfhe_b200_circuit_eval_batch(self.h, g.ctypes.data, len(g), _ptr(wires), n_wires, count, self._stream(stream)), "circuit_eval")
 
     def bootsGate_host(self, op, result_host, ca_host, cb_host, count):
         op = GATES[op] if isinstance(op, str) else op

@@ -322,6 +322,62 @@ int tfhe_b200_bootsGate_batch_host(tfhe_b200_ctx* ctx, int op, int32_t* result_h
     return TFHE_B200_OK;
 }
 
+/* ------------------------------------------------------------------ gate-level circuits */
+int tfhe_b200_circuit_eval_batch(tfhe_b200_ctx* ctx, const tfhe_b200_gate* gates, int n_gates, int32_t* wires_dev, int n_wires,
+                                 int count, void* stream) {
+    NEED_GATE(); NEED(n_gates >= 0 && n_wires >= 0 && count >= 0, "circuit_eval: negative size");
+    NEED(n_gates == 0 || gates, "circuit_eval: null netlist"); NEED(n_gates == 0 || count == 0 || wires_dev, "circuit_eval: null wires");
+    if (count == 0) return TFHE_B200_OK;
+    const size_t wstride = (size_t)count * (ctx->gp.n + 1);
+    auto arity = [](int op) { return op == TFHE_B200_MUX ? 3 : (op == TFHE_B200_NOT || op == TFHE_B200_COPY ? 1 : 2); };
+    for (int i = 0; i < n_gates; i++) {
+        const tfhe_b200_gate& g = gates[i];
+        NEED((g.op >= 0 && g.op < TFHE_B200_NUM_GATES) || g.op == TFHE_B200_NOT || g.op == TFHE_B200_COPY || g.op == TFHE_B200_MUX,
+             "circuit_eval: unknown op");
+        const int ar = arity(g.op);
+        NEED(g.out >= 0 && g.out < n_wires && g.in0 >= 0 && g.in0 < n_wires && (ar < 2 || (g.in1 >= 0 && g.in1 < n_wires)) &&
+             (ar < 3 || (g.in2 >= 0 && g.in2 < n_wires)), "circuit_eval: wire index out of range");
+    }
+    for (int i = 0; i < n_gates;) {
+        const tfhe_b200_gate& g = gates[i];
+        const int ar = arity(g.op);
+        // longest run of "the same gate on the next wires" that keeps the gates independent of each other
+        int run = 1;
+        while (i + run < n_gates) {
+            const tfhe_b200_gate& h = gates[i + run];
+            if (h.op != g.op || h.out != g.out + run || h.in0 != g.in0 + run || (ar >= 2 && h.in1 != g.in1 + run) ||
+                (ar >= 3 && h.in2 != g.in2 + run)) break;
+            auto reads_run_output = [&](int w) { return w >= g.out && w < g.out + run; };     // outputs of gates i .. i+run-1
+            if (reads_run_output(h.in0) || (ar >= 2 && reads_run_output(h.in1)) || (ar >= 3 && reads_run_output(h.in2))) break;
+            // and no earlier gate of the run may read what this one writes later (write-after-read inside one launch is fine:
+            // every launch reads all its inputs before the key switch writes, but keep the semantics of sequential execution)
+            bool war = false;
+            for (int j = 0; j < run && !war; j++) {
+                const tfhe_b200_gate& e = gates[i + j];
+                war = e.in0 == h.out || (ar >= 2 && e.in1 == h.out) || (ar >= 3 && e.in2 == h.out);
+            }
+            if (war) break;
+            run++;
+        }
+        const long total = (long)run * count;
+        NEED(total <= 0x7fffffffL, "circuit_eval: run * count overflows");
+        int32_t* out = wires_dev + (size_t)g.out * wstride;
+        const int32_t* a = wires_dev + (size_t)g.in0 * wstride;
+        const int32_t* b = ar >= 2 ? wires_dev + (size_t)g.in1 * wstride : nullptr;
+        const int32_t* c = ar >= 3 ? wires_dev + (size_t)g.in2 * wstride : nullptr;
+        int rc;
+        if (g.op == TFHE_B200_NOT) rc = tfhe_b200_bootsNOT_batch(ctx, out, a, (int)total, stream);
+        else if (g.op == TFHE_B200_COPY) {
+            rc = TFHE_B200_OK;
+            if (out != a) CU(cudaMemcpyAsync(out, a, (size_t)total * (ctx->gp.n + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        } else if (g.op == TFHE_B200_MUX) rc = tfhe_b200_bootsMUX_batch(ctx, out, a, b, c, (int)total, stream);
+        else rc = tfhe_b200_bootsGate_batch(ctx, g.op, out, a, b, (int)total, stream);
+        if (rc) return rc;
+        i += run;
+    }
+    return TFHE_B200_OK;
+}
+
 /* ------------------------------------------------------------------ standalone transforms */
 static const cplx* tw_for(const tfhe_b200_ctx* ctx, int N) { return N == 1024 ? ctx->tw1024 : (N == 2048 ? ctx->tw2048 : nullptr); }
 

@@ -324,4 +324,31 @@ inline void tfhe_CircuitBootstrapFFT(TGswSample32* result, const LweSample32* sa
         memcpy(result->samples[u][w]->a[q].coefs, out.data() + (((size_t)u * l1 + w) * 2 + q) * N1, sizeof(Torus32) * N1);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Gate-level circuits (BASELINE configs[2]; no reference counterpart, see include/tfhe_b200.h: tfhe_b200_circuit_eval_batch).
+// Ripple-carry adder, `bits` wide: per bit t = a^b, g = a&b, s = t^c, p = t&c, c' = g|p  (2 XOR + 2 AND + 1 OR = 5 bootstrapped
+// gates per bit).  Wire map: a[i] = i, b[i] = bits+i, cin = 2 bits, s[i] = 2 bits+1+i, cout = c[bits];
+// internal t, g, c follow.  The 2*bits level-0 gates come first and merge into two launches of bits*count samples.
+// ---------------------------------------------------------------------------------------------------------------
+struct AdderNetlist {
+    int bits, n_wires;
+    int a0, b0, cin, s0, c0;          // first wire of each bus; carry c[i] = c0 + i, c[0] = cin copied, cout = c0 + bits
+    std::vector<tfhe_b200_gate> gates;
+};
+inline AdderNetlist ripple_carry_adder_netlist(int bits) {
+    AdderNetlist nl;
+    nl.bits = bits; nl.a0 = 0; nl.b0 = bits; nl.cin = 2 * bits; nl.s0 = 2 * bits + 1;
+    const int t0 = nl.s0 + bits, g0 = t0 + bits, p0 = g0 + bits;
+    nl.c0 = p0 + bits; nl.n_wires = nl.c0 + bits + 1;
+    for (int i = 0; i < bits; i++) nl.gates.push_back({TFHE_B200_XOR, t0 + i, nl.a0 + i, nl.b0 + i, 0});
+    for (int i = 0; i < bits; i++) nl.gates.push_back({TFHE_B200_AND, g0 + i, nl.a0 + i, nl.b0 + i, 0});
+    nl.gates.push_back({TFHE_B200_COPY, nl.c0, nl.cin, 0, 0});
+    for (int i = 0; i < bits; i++) {
+        nl.gates.push_back({TFHE_B200_XOR, nl.s0 + i, t0 + i, nl.c0 + i, 0});
+        nl.gates.push_back({TFHE_B200_AND, p0 + i, t0 + i, nl.c0 + i, 0});
+        nl.gates.push_back({TFHE_B200_OR, nl.c0 + i + 1, g0 + i, p0 + i, 0});
+    }
+    return nl;
+}
+
 }  // namespace tfhe_b200_compat

@@ -108,6 +108,19 @@ int tfhe_b200_bootsMUX_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int3
 int tfhe_b200_bootsGate_batch_host(tfhe_b200_ctx* ctx, int op, int32_t* result_host, const int32_t* ca_host,
                                    const int32_t* cb_host, int count);
 
+/* Gate-level circuits (BASELINE configs[2], SURVEY.md 8d "Config 3" / 8f rank 2; the reference has no circuit layer -- a
+ * circuit evaluator over it would be a loop of upstream boots* calls, one sample at a time).
+ * A WIRE is a batch of `count` LWE samples, wires_dev[wire][count][n+1]: `count` independent instances of the same netlist
+ * run side by side.  Gates execute in the order given (the caller supplies a topological order); a run of consecutive gates
+ * with the same op whose wires advance by one per gate (out+j, in0+j, in1+j, no gate of the run reading another's output)
+ * is merged into ONE batched launch of run*count samples -- e.g. the 32 a_i XOR b_i of an adder.  All launches go to
+ * `stream`; after a first (warm-up) call nothing is allocated, so the call can be captured into a CUDA graph.
+ * op: TFHE_B200_NAND .. TFHE_B200_ORYN (in0, in1), TFHE_B200_NOT / TFHE_B200_COPY (in0), TFHE_B200_MUX (in0 ? in1 : in2). */
+enum { TFHE_B200_NOT = 16, TFHE_B200_COPY = 17, TFHE_B200_MUX = 18 };
+typedef struct { int32_t op, out, in0, in1, in2; } tfhe_b200_gate;
+int tfhe_b200_circuit_eval_batch(tfhe_b200_ctx* ctx, const tfhe_b200_gate* gates_host, int n_gates,
+                                 int32_t* wires_dev, int n_wires, int count, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Negacyclic FP64 transforms (cb/spqlios/fft_processor_spqlios.cpp).  The spectral ("LagrangeHalfC")
  * layout is engine-private, exactly as the reference's is private to spqlios: N doubles per
