@@ -70,6 +70,10 @@ _SIGS = {
     "tfhe_b200_bootsNOT_batch": [_P, _P, _P, _I, _P],
     "tfhe_b200_bootsMUX_batch": [_P, _P, _P, _P, _P, _I, _P],
     "tfhe_b200_circuit_eval_batch": [_P, _P, _I, _P, _I, _I, _P],
+    "tfhe_b200_tGswToFFTConvert_batch": [_P, _P, _P, _I, _I, _P],
+    "tfhe_b200_tGswFFTExternMulToTLwe_batch": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "tfhe_b200_CMux_batch": [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P],
+    "tfhe_b200_LUT_vertical_packing_batch": [_P, _P, _P, _I, _P, _I, _I, _I, _P],
     "tfhe_b200_bootsGate_batch_host": [_P, _I, _P, _P, _P, _I],
     "tfhe_b200_IntPolynomial_ifft_batch": [_P, _P, _P, _I, _I, _P],
     "tfhe_b200_TorusPolynomial64_ifft_batch": [_P, _P, _P, _I, _I, _P],
@@ -251,6 +255,22 @@ class Engine:
     def bootsGate_host(self, op, result_host, ca_host, cb_host, count):
         op = GATES[op] if isinstance(op, str) else op
         self._ck(self.lib.tfhe_b200_bootsGate_batch_host(self.h, op, _ptr(result_host), _ptr(ca_host), _ptr(cb_host), count), "bootsGate_host")
+
+    # ------------------------------------------------------------------ TRGSW x TRLWE (N = 1024, Torus32)
+    def tGswToFFTConvert(self, gswfft, gsw, l, count, stream=None):
+        self._ck(self.lib.tfhe_b200_tGswToFFTConvert_batch(self.h, _ptr(gswfft), _ptr(gsw), l, count, self._stream(stream)), "tGswToFFTConvert")
+
+    def tGswFFTExternMulToTLwe(self, accum, gswfft, per_sample, l, Bgbit, count, stream=None):
+        self._ck(self.lib.tfhe_b200_tGswFFTExternMulToTLwe_batch(self.h, _ptr(accum), _ptr(gswfft), int(per_sample), l, Bgbit, count,
+                                                                 self._stream(stream)), "tGswFFTExternMulToTLwe")
+
+    def CMux(self, result, gswfft, per_sample, d1, d0, l, Bgbit, count, stream=None):
+        self._ck(self.lib.tfhe_b200_CMux_batch(self.h, _ptr(result), _ptr(gswfft), int(per_sample), _ptr(d1), _ptr(d0), l, Bgbit, count,
+                                               self._stream(stream)), "CMux")
+
+    def LUT_vertical_packing(self, result, selfft, nsel, table, l, Bgbit, count, stream=None):
+        self._ck(self.lib.tfhe_b200_LUT_vertical_packing_batch(self.h, _ptr(result), _ptr(selfft), nsel, _ptr(table), l, Bgbit, count,
+                                                               self._stream(stream)), "LUT_vertical_packing")
 
     # ------------------------------------------------------------------ transforms
     def IntPolynomial_ifft(self, result, poly, N, count, stream=None):

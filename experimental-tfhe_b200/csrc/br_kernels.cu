@@ -180,7 +180,9 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
 // reads, index and sign arithmetic) and parked in this lane's tensor-memory columns [128, 128 + 32 words); levels 1.. only
 // reload it and cut their digit.  Otherwise every level re-reads the accumulator.
 template <typename Torus> struct StashWords { static constexpr int PER_C = 8 * (int)(sizeof(Torus) / 4); };   // words per c (4 complex)
-template <int LOGM, typename Torus, bool STASH, bool ALLREG>
+// PLAIN: the external product alone, ACC <- BK (x) ACC (tGswFFTExternMulToTLwe, cb/tgsw_functions.cpp:424-449): no rotation
+// on the way in, no accumulation on the way out.
+template <int LOGM, typename Torus, bool STASH, bool ALLREG, bool PLAIN = false>
 __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, const cplx* __restrict__ bk,
                                           const int l, const int Bgbit, cplx* __restrict__ buf, const uint32_t tacc,
                                           KeyPipe& kp, const cplx* __restrict__ tw, const int t, const int bar_id) {
@@ -229,8 +231,8 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int j = t + T * (4 * c + i);
-                    const U ure = (U)rot_minus_one<Torus, N>(aq, j, a2) + offset;
-                    const U uim = (U)rot_minus_one<Torus, N>(aq, j + M, a2) + offset;
+                    const U ure = (U)(PLAIN ? aq[j] : rot_minus_one<Torus, N>(aq, j, a2)) + offset;
+                    const U uim = (U)(PLAIN ? aq[j + M] : rot_minus_one<Torus, N>(aq, j + M, a2)) + offset;
                     v[4 * c + i] = make_double2((double)((int)((uint32_t)(ure >> sh) & mask) - half),
                                                 (double)((int)((uint32_t)(uim >> sh) & mask) - half));
                     if (STASH) {
@@ -260,8 +262,8 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
 #pragma unroll
         for (int m = 0; m < 16; m++) {
             const int j = t + T * m;
-            acc[j] = (Torus)((U)acc[j] + (U)to_torus(R[m].x, (Torus)0));
-            acc[j + M] = (Torus)((U)acc[j + M] + (U)to_torus(R[m].y, (Torus)0));
+            acc[j] = (Torus)((PLAIN ? (U)0 : (U)acc[j]) + (U)to_torus(R[m].x, (Torus)0));
+            acc[j + M] = (Torus)((PLAIN ? (U)0 : (U)acc[j + M]) + (U)to_torus(R[m].y, (Torus)0));
         }
         TL(14);
     }
@@ -273,8 +275,8 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
 #pragma unroll
         for (int m = 0; m < 16; m++) {
             const int j = t + T * m;
-            acc[N + j] = (Torus)((U)acc[N + j] + (U)to_torus(R[m].x, (Torus)0));
-            acc[N + j + M] = (Torus)((U)acc[N + j + M] + (U)to_torus(R[m].y, (Torus)0));
+            acc[N + j] = (Torus)((PLAIN ? (U)0 : (U)acc[N + j]) + (U)to_torus(R[m].x, (Torus)0));
+            acc[N + j + M] = (Torus)((PLAIN ? (U)0 : (U)acc[N + j + M]) + (U)to_torus(R[m].y, (Torus)0));
         }
         TL(14);
     }
@@ -429,6 +431,62 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// One external product per sample: accum_b <- G_b (x) accum_b  (tGswFFTExternMulToTLwe, cb/tgsw_functions.cpp:424-449).
+// Same lane-group machinery as a blind-rotation step (decomposition, 2l forward transforms, multiply-accumulates in tensor
+// memory, 2 backward transforms); the TGSW spectra are per sample (circuit-bootstrapped selectors of a LUT)
+// or shared (stride 0).
+// ---------------------------------------------------------------------------------------------
+template <int LOGM, typename Torus, int GROUPS>
+__global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) extern_mul_kernel(const BRArgs A) {
+    typedef TreePlan<LOGM> P;
+    typedef BRSmem<LOGM, Torus, GROUPS, true, true> S;
+    constexpr int N = P::N, T = P::T;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx* tw = reinterpret_cast<cplx*>(smem_raw);
+    const int g = threadIdx.x / T, t = threadIdx.x % T, warp = threadIdx.x >> 5;
+    const int bar_id = 1 + g;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(smem_raw + S::TW_BYTES + 64);
+    unsigned char* gbase = smem_raw + S::GROUPS_OFF + (size_t)g * S::GROUP_BYTES;
+    cplx* buf = reinterpret_cast<cplx*>(gbase);
+    Torus* acc = reinterpret_cast<Torus*>(gbase + S::BUF_BYTES);
+    for (int i = threadIdx.x; i < P::TW_TOTAL; i += GROUPS * T) tw[i] = A.tw[i];
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_base_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_slot;
+    const uint32_t tacc = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)S::TMEM_COLS;
+    const long unit = (long)blockIdx.x * GROUPS + g;
+    if (unit < A.count) {
+        Torus* io = reinterpret_cast<Torus*>(A.accum) + (size_t)unit * 2 * N;
+        for (int j = t; j < 2 * N; j += T) acc[j] = io[j];
+        lanes_sync<T>(bar_id);
+        KeyPipe kp{};       // unused on the register-prefetch path
+        cmux_step<LOGM, Torus, true, true, true>(acc, 1, A.bkfft + (size_t)(unit / (A.units_per_gsw > 0 ? A.units_per_gsw : 1)) * A.bk_sample_stride, A.l, A.Bgbit, buf, tacc, kp, tw, t, bar_id);
+        for (int j = t; j < 2 * N; j += T) io[j] = acc[j];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+cudaError_t launch_extern_mul32(const BRArgs& a, cudaStream_t s) {
+    constexpr int G = 8;
+    typedef BRSmem<9, int32_t, G, true, true> S;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(extern_mul_kernel<9, int32_t, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    if (a.count <= 0) return cudaSuccess;
+    extern_mul_kernel<9, int32_t, G><<<(a.count + G - 1) / G, G * TreePlan<9>::T, S::TOTAL, s>>>(a);
+    return cudaGetLastError();
 }
 
 #ifdef BR_TIMELINE

@@ -322,6 +322,87 @@ int tfhe_b200_bootsGate_batch_host(tfhe_b200_ctx* ctx, int op, int32_t* result_h
     return TFHE_B200_OK;
 }
 
+/* ------------------------------------------------------------------ TRGSW x TRLWE products (N = 1024, Torus32) */
+static int check_gadget(tfhe_b200_ctx* ctx, int l, int Bgbit) {
+    NEED(l >= 1 && Bgbit >= 1 && Bgbit <= 16 && l * Bgbit <= 32, "bad gadget (l, Bgbit)");
+    return TFHE_B200_OK;
+}
+int tfhe_b200_tGswToFFTConvert_batch(tfhe_b200_ctx* ctx, double* gswfft_dev, const int32_t* gsw_dev, int l, int count, void* stream) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(l >= 1 && l <= 32, "tGswToFFTConvert: bad l"); NEED(count >= 0, "count < 0"); NEED(count == 0 || (gswfft_dev && gsw_dev), "null buffer");
+    const long npoly = (long)count * 2 * l * 2;
+    NEED(npoly <= 0x7fffffffL, "tGswToFFTConvert: too many polynomials");
+    CU(launch_poly_to_spectrum32((cplx*)gswfft_dev, gsw_dev, ctx->tw1024, 1024, (int)npoly, 2.0 / 1024, (cudaStream_t)stream));
+    return TFHE_B200_OK;
+}
+static int extmul(tfhe_b200_ctx* ctx, int32_t* accum_dev, const double* gswfft_dev, size_t stride, int units_per_gsw, int l, int Bgbit,
+                  long count, cudaStream_t s) {
+    NEED(count <= 0x7fffffffL, "extern mul: batch too large");
+    BRArgs a{};
+    a.bkfft = (const cplx*)gswfft_dev; a.tw = ctx->tw1024; a.l = l; a.Bgbit = Bgbit; a.count = (int)count; a.mode = BR_EXTMUL;
+    a.accum = accum_dev; a.bk_sample_stride = stride; a.units_per_gsw = units_per_gsw;
+    { ProfScope ps(ctx, 0, s); CU(launch_extern_mul32(a, s)); }
+    return TFHE_B200_OK;
+}
+int tfhe_b200_tGswFFTExternMulToTLwe_batch(tfhe_b200_ctx* ctx, int32_t* accum_dev, const double* gswfft_dev, int per_sample,
+                                           int l, int Bgbit, int count, void* stream) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    int rc = check_gadget(ctx, l, Bgbit); if (rc) return rc;
+    NEED(count >= 0, "count < 0"); NEED(count == 0 || (accum_dev && gswfft_dev), "null buffer");
+    return extmul(ctx, accum_dev, gswfft_dev, per_sample ? (size_t)2 * l * 2 * 512 : 0, 1, l, Bgbit, count, (cudaStream_t)stream);
+}
+int tfhe_b200_CMux_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const double* gswfft_dev, int per_sample, const int32_t* d1_dev,
+                         const int32_t* d0_dev, int l, int Bgbit, int count, void* stream) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    int rc = check_gadget(ctx, l, Bgbit); if (rc) return rc;
+    NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && gswfft_dev && d1_dev && d0_dev), "null buffer");
+    if (count == 0) return TFHE_B200_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int len = 2 * 1024;
+    const size_t bytes = (size_t)count * len * sizeof(int32_t);
+    rc = ensure_scratch(ctx, 0, bytes); if (rc) return rc;
+    int32_t* tmp = (int32_t*)ctx->scratch[0];
+    // tmp = d1 - d0 ; tmp <- C (x) tmp ; result = tmp + d0      (flat rows of len int32; the lincomb constant is 0)
+    { ProfScope ps(ctx, 2, s); CU(launch_lwe_lincomb(tmp, d1_dev, d0_dev, 1, -1, 0, len - 1, count, s)); }
+    rc = extmul(ctx, tmp, gswfft_dev, per_sample ? (size_t)2 * l * 2 * 512 : 0, 1, l, Bgbit, count, s); if (rc) return rc;
+    { ProfScope ps(ctx, 2, s); CU(launch_lwe_lincomb(result_dev, tmp, d0_dev, 1, 1, 0, len - 1, count, s)); }
+    return TFHE_B200_OK;
+}
+int tfhe_b200_LUT_vertical_packing_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const double* selfft_dev, int nsel,
+                                         const int32_t* table_dev, int l, int Bgbit, int count, void* stream) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    int rc = check_gadget(ctx, l, Bgbit); if (rc) return rc;
+    NEED(nsel >= 1 && nsel <= 16, "LUT: nsel must be 1..16"); NEED(count >= 0, "count < 0");
+    NEED(count == 0 || (result_dev && selfft_dev && table_dev), "null buffer");
+    if (count == 0) return TFHE_B200_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int N = 1024, len = 2 * N;
+    const size_t gsw_cplx = (size_t)2 * l * 2 * 512;                 // one TGSW spectrum
+    const size_t lvl0_units = (size_t)count << (nsel - 1);
+    NEED(lvl0_units <= 0x7fffffffUL, "LUT: count * 2^(nsel-1) too large");
+    // ping-pong level buffers: level j produces count * 2^(nsel-1-j) TRLWE of len int32
+    rc = ensure_scratch(ctx, 0, lvl0_units * len * sizeof(int32_t)); if (rc) return rc;
+    rc = ensure_scratch(ctx, 1, (lvl0_units / 2 + 1) * len * sizeof(int32_t)); if (rc) return rc;
+    int32_t* pp[2] = {(int32_t*)ctx->scratch[0], (int32_t*)ctx->scratch[1]};
+    const int32_t* in = nullptr;
+    for (int j = 0; j < nsel; j++) {
+        const int nodes = 1 << (nsel - 1 - j);
+        const size_t units = (size_t)count * nodes;
+        int32_t* out = (j == nsel - 1) ? result_dev : pp[j & 1];
+        // out = d1 - d0 : level 0 straight from the plaintext table (trivial TRLWE, the same for every sample), then from pairs
+        if (j == 0) { ProfScope ps(ctx, 2, s); CU(launch_lut_table(out, table_dev, N, nodes, count, 0, s)); }
+        else        { ProfScope ps(ctx, 2, s); CU(launch_pair_combine(out, in, len, units, 0, s)); }
+        // out <- sel_j (x) out ; the TGSW of unit u is selector j of sample u / nodes
+        rc = extmul(ctx, out, selfft_dev + (size_t)j * gsw_cplx * 2 /* doubles per cplx */, (size_t)nsel * gsw_cplx, nodes, l, Bgbit, (long)units, s);
+        if (rc) return rc;
+        // out += d0
+        if (j == 0) { ProfScope ps(ctx, 2, s); CU(launch_lut_table(out, table_dev, N, nodes, count, 1, s)); }
+        else        { ProfScope ps(ctx, 2, s); CU(launch_pair_combine(out, in, len, units, 1, s)); }
+        in = out;
+    }
+    return TFHE_B200_OK;
+}
+
 /* ------------------------------------------------------------------ gate-level circuits */
 int tfhe_b200_circuit_eval_batch(tfhe_b200_ctx* ctx, const tfhe_b200_gate* gates, int n_gates, int32_t* wires_dev, int n_wires,
                                  int count, void* stream) {

@@ -16,7 +16,7 @@ int  fft_table_entries(int logM);
 void make_hp_tables(int n2N, int inverse, uint64_t* out /* 4 * n2N words */);
 
 // ------------------------------------------------------------------ blind rotation (br_kernels.cu)
-enum BRMode { BR_ACCUM = 0, BR_TESTVEC = 1, BR_LWE = 2 };
+enum BRMode { BR_ACCUM = 0, BR_TESTVEC = 1, BR_LWE = 2, BR_EXTMUL = 3 };
 struct BRArgs {
     const cplx* bkfft;    // [n][2l][2][M] spectra, pre-scaled by 2/N
     const cplx* tw;       // TreePlan table
@@ -24,6 +24,8 @@ struct BRArgs {
     // BR_ACCUM  : accum[B][2][N] in/out, bara[B][n]
     // BR_TESTVEC: v[N], barb[B], bara[B][n] -> out[B][N+1]
     // BR_LWE    : x = (0,cconst) + ka*xa + kb*xb (LWE(n) samples, xb may be null), test vector = mu -> out[B][N+1]
+    // BR_EXTMUL : accum[B][2][N] <- G_b (x) accum_b, one external product per sample, G_b = bkfft + b * bk_sample_stride
+    //             (tGswFFTExternMulToTLwe, cb/tgsw_functions.cpp:424-449); n, bara unused
     void* accum;
     const int32_t* bara;
     const int32_t* barb;
@@ -37,10 +39,13 @@ struct BRArgs {
     int out_stride;       // elements between consecutive outputs (N+1 by default)
     // Torus64 (circuit bootstrap) only: number of test vectors sharing one pass (mu_w = 2^(64-(w+1)*bgbit1))
     int n_mu; int mu_bgbit;
+    size_t bk_sample_stride;   // BR_EXTMUL: cplx elements between the TGSW spectra of consecutive samples (0: one TGSW for all)
+    int units_per_gsw;         // BR_EXTMUL: consecutive accumulators sharing one TGSW (nodes of a LUT level); 0 = 1
 };
 cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s);     // N = 1024, Torus32
 cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s);     // N = 2048, Torus64 (circuitBootstrapWoKS)
 cudaError_t blind_rotate_init();                                         // opt-in shared memory sizes
+cudaError_t launch_extern_mul32(const BRArgs& a, cudaStream_t s);        // BR_EXTMUL, N = 1024, Torus32
 
 // coefficient polynomials -> spectra in engine order; scale applied to the output
 cudaError_t launch_poly_to_spectrum32(cplx* out, const int32_t* in, const cplx* tw, int N, int count, double scale, cudaStream_t s);
@@ -78,6 +83,10 @@ cudaError_t launch_lwe_lincomb(int32_t* out, const int32_t* a, const int32_t* b,
                                int n, int count, cudaStream_t s);   // out = (0,cconst) + ka*a + kb*b   (b may be null)
 cudaError_t probe_fp64(double* tflops);
 cudaError_t probe_read(size_t bytes, int passes, double* gbs);
+// TRLWE pair steps of a CMUX tree over flat units of `len` int32: mode 0: out[u] = in[2u+1] - in[2u]; mode 1: out[u] += in[2u]
+cudaError_t launch_pair_combine(int32_t* out, const int32_t* in, int len, size_t units, int mode, cudaStream_t s);
+// LUT level 0 from a plaintext table: mode 0: out[c][i] = trivial TRLWE (0, table[2i+1] - table[2i]); mode 1: out[c][i].b += table[2i]
+cudaError_t launch_lut_table(int32_t* out, const int32_t* table, int N, int pairs, int count, int mode, cudaStream_t s);
 cudaError_t launch_modswitch(int32_t* out, const int32_t* in, int Msize_log2, size_t total, cudaStream_t s);
 
 // ------------------------------------------------------------------ high-precision FFT (hp_kernels.cu)

@@ -22,6 +22,40 @@ cudaError_t launch_lwe_lincomb(int32_t* out, const int32_t* a, const int32_t* b,
     return cudaGetLastError();
 }
 
+// CMUX tree helpers (vertical-packing LUT on TRGSW selectors): CMux(C, d1, d0) = C (x) (d1 - d0) + d0
+__global__ void pair_combine_kernel(int32_t* __restrict__ out, const int32_t* __restrict__ in, int len, size_t total, int mode) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t u = e / len; const int k = (int)(e % len);
+        const uint32_t d0 = (uint32_t)in[(2 * u) * len + k];
+        if (mode == 0) out[e] = (int32_t)((uint32_t)in[(2 * u + 1) * len + k] - d0);
+        else out[e] = (int32_t)((uint32_t)out[e] + d0);
+    }
+}
+cudaError_t launch_pair_combine(int32_t* out, const int32_t* in, int len, size_t units, int mode, cudaStream_t s) {
+    const size_t total = units * (size_t)len;
+    if (!total) return cudaSuccess;
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    pair_combine_kernel<<<grid, 256, 0, s>>>(out, in, len, total, mode);
+    return cudaGetLastError();
+}
+// mode 0: out[c][i] = trivial TRLWE (0, table[2i+1] - table[2i]) ; mode 1: out[c][i].b += table[2i]     (i < pairs, every sample c)
+__global__ void lut_table_kernel(int32_t* __restrict__ out, const int32_t* __restrict__ table, int N, int pairs, size_t total, int mode) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e % (2 * N)); const int i = (int)((e / (2 * N)) % pairs);
+        if (k < N) { if (mode == 0) out[e] = 0; continue; }
+        const uint32_t even = (uint32_t)table[(size_t)(2 * i) * N + (k - N)];
+        if (mode == 0) out[e] = (int32_t)((uint32_t)table[(size_t)(2 * i + 1) * N + (k - N)] - even);
+        else out[e] = (int32_t)((uint32_t)out[e] + even);
+    }
+}
+cudaError_t launch_lut_table(int32_t* out, const int32_t* table, int N, int pairs, int count, int mode, cudaStream_t s) {
+    const size_t total = (size_t)count * pairs * 2 * N;
+    if (!total) return cudaSuccess;
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16;
+    lut_table_kernel<<<grid, 256, 0, s>>>(out, table, N, pairs, total, mode);
+    return cudaGetLastError();
+}
+
 // modSwitchFromTorus32 (cb/numeric_functions.cpp:54-60) / preModSwitch (cb/poc_CircuitBootstrapping.cpp:472-484), Msize = 2^k
 __global__ void modswitch_kernel(int32_t* __restrict__ out, const int32_t* __restrict__ in, int log2Msize, size_t total) {
     const uint64_t half = 1ull << (63 - log2Msize);

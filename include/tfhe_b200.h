@@ -144,6 +144,28 @@ int tfhe_b200_LagrangeHalfCPolynomialAddMul_batch(tfhe_b200_ctx* ctx, double* re
                                                   const double* b_dev, int N, int count, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * TRGSW x TRLWE products at N = 1024, Torus32 (what the TRGSW outputs of a circuit bootstrap feed).
+ * A TGSW sample is [2l][2][N] int32 (rows p = bloc*l + i, cb/poc_types.h:206-234) -- exactly one [u][w] block of
+ * tfhe_b200_CircuitBootstrapFFT_batch's output; its spectral form is [2l][2][N doubles], engine-private layout.
+ * ---------------------------------------------------------------------------------------------- */
+/* tGswToFFTConvert (cb/tgsw_functions.cpp:389-394): count TGSW samples -> spectra (scaled by 2/N for the product below). */
+int tfhe_b200_tGswToFFTConvert_batch(tfhe_b200_ctx* ctx, double* gswfft_dev, const int32_t* gsw_dev, int l,
+                                     int count, void* stream);
+/* tGswFFTExternMulToTLwe (cb/tgsw_functions.cpp:424-449): accum[b] <- G (x) accum[b], accum [count][2][N] in place.
+ * per_sample != 0: G = gswfft[b]; per_sample == 0: one G for the whole batch. */
+int tfhe_b200_tGswFFTExternMulToTLwe_batch(tfhe_b200_ctx* ctx, int32_t* accum_dev, const double* gswfft_dev, int per_sample,
+                                           int l, int Bgbit, int count, void* stream);
+/* CMux(C, d1, d0) = C (x) (d1 - d0) + d0 (the reference's commented stub, cb/poc_CircuitBootstrapping.cpp:877-879):
+ * result, d1, d0 are TRLWE batches [count][2][N]; result may alias d1 or d0. */
+int tfhe_b200_CMux_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const double* gswfft_dev, int per_sample,
+                         const int32_t* d1_dev, const int32_t* d0_dev, int l, int Bgbit, int count, void* stream);
+/* Vertical-packing look-up: for every sample b, result[b] = TRLWE of table[ sum_j bit_j(b) 2^j ], selected by a CMUX tree
+ * over its nsel TRGSW selector bits sel[b][j] (spectral form, [count][nsel][2l][2][N doubles]); table: 2^nsel plaintext
+ * polynomials [2^nsel][N] int32 shared by the batch (BASELINE configs[3] "feeding a vertical-packing LUT"). */
+int tfhe_b200_LUT_vertical_packing_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const double* selfft_dev, int nsel,
+                                         const int32_t* table_dev, int l, int Bgbit, int count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Circuit bootstrapping (cb/poc_CircuitBootstrapping.cpp), LWE32(N1) -> TRGSW32(N1)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {

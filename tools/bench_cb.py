@@ -52,5 +52,16 @@ out["circuit_bootstrap"] = {"batch": B, "ms": t_cb, "cb_per_s": B / t_cb * 1e3, 
                             "blind_rotate_ms": ms["blind_rotate"] / 3, "keyswitch_ms": ms["keyswitch"] / 3,
                             "fp64_tflops_blind_rotate": 352.3e6 * 2 * B / (ms["blind_rotate"] / 3 * 1e-3) / 1e12}
 print(json.dumps({"circuit_bootstrap": out["circuit_bootstrap"]}), flush=True)
+# ---------------- config 4 continued: the TRGSW outputs feed a vertical-packing LUT (8 selector bits per look-up, 256-entry table)
+nsel = 8
+L = B // nsel
+selfft = torch.empty((L * nsel, 2 * ell1, 2, c.N1), dtype=torch.float64, device="cuda")
+table = torch.randint(-2**31, 2**31 - 1, (1 << nsel, c.N1), dtype=torch.int64, device="cuda").to(torch.int32)
+lut = torch.empty((L, 2, c.N1), dtype=torch.int32, device="cuda")
+t_conv = timeit(lambda: eng.tGswToFFTConvert(selfft, res, ell1, L * nsel))
+t_lut = timeit(lambda: eng.LUT_vertical_packing(lut, selfft, nsel, table, ell1, c.params.bgbit_lvl1, L))
+out["lut_vertical_packing"] = {"lookups": L, "selector_bits": nsel, "tGswToFFTConvert_ms": t_conv, "lut_ms": t_lut,
+                               "cmux_per_s": L * ((1 << nsel) - 1) / t_lut * 1e3, "lookups_per_s": L / t_lut * 1e3}
+print(json.dumps({"lut_vertical_packing": out["lut_vertical_packing"]}), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "bench_cb_hp.json"), "w"), indent=1)
