@@ -131,18 +131,49 @@ __device__ __forceinline__ void load_tmem(cplx (&R)[16], const uint32_t taddr) {
 }
 
 // forward transform of one digit polynomial + its two multiply-accumulates.
-//   ALLREG : both key polynomials are prefetched into registers with ld.global.nc right after depths 4-7 (8 warps per SM)
-//   else   : they wait in tensor memory (KeyPipe, bk_pipe.cuh), no key registers at all (12 warps per SM)
-template <int LOGM, bool FIRST, bool ALLREG>
+//   KM_REGS2: both key polynomials are prefetched into registers with ld.global.nc right after depths 4-7 (8 warps per SM)
+//   KM_REGS1: one key polynomial's worth of registers: BK[p][0] is prefetched the same way, and as the first multiply-accumulate
+//             consumes it, chunk by chunk, the freed registers take BK[p][1] (12 warps per SM at 168 registers)
+//   KM_TMEM : they wait in tensor memory (KeyPipe, bk_pipe.cuh), no key registers at all (12 warps per SM)
+enum { KM_REGS2 = 0, KM_TMEM = 1, KM_REGS1 = 2 };
+template <int LOGM, bool FIRST, int KM>
 __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t tacc, const cplx* __restrict__ bkp,
                                                 cplx* __restrict__ buf, KeyPipe& kp,
                                                 const cplx* __restrict__ tw, const int t, const int bar_id) {
     typedef TreePlan<LOGM> P;
     tree_forward_a<LOGM>(v, buf, tw, t, bar_id);
-    if (!ALLREG && (t & 31) == 0) kp.poll();
+    if (KM == KM_TMEM && (t & 31) == 0) kp.poll();
     tree_forward_b<LOGM>(v, tw, t);
     TL(4);
-    if (ALLREG) {
+    if (KM == KM_REGS1) {
+        const cplx* __restrict__ g0 = bkp + t;
+        asm volatile("" : "+l"(g0) : "d"(v[0].x), "d"(v[15].y));          // do not hoist the loads above the pass
+        cplx kb[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) kb[i] = __ldg(g0 + i * P::T);
+        tree_forward_c<LOGM>(v, tw, t);
+        TL(6);
+        // R0 += v * BK[p][0]; each consumed chunk's registers are refilled with the same slots of BK[p][1]
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t r[16];
+            if (!FIRST) { TFHE_TLD16(r, tacc + 16 * c); tmem_wait_ld(); }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                cplx R = FIRST ? make_double2(0.0, 0.0)
+                               : make_double2(__hiloint2double((int)r[4 * i + 1], (int)r[4 * i]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]));
+                cfma(R, v[4 * c + i], kb[4 * c + i]);
+                r[4 * i] = (uint32_t)__double2loint(R.x); r[4 * i + 1] = (uint32_t)__double2hiint(R.x);
+                r[4 * i + 2] = (uint32_t)__double2loint(R.y); r[4 * i + 3] = (uint32_t)__double2hiint(R.y);
+            }
+            TFHE_TST16(r, tacc + 16 * c);
+#pragma unroll
+            for (int i = 0; i < 4; i++) kb[4 * c + i] = __ldg(g0 + P::M + (4 * c + i) * P::T);
+        }
+        TL(7);
+        mac_tmem<FIRST>(tacc + 64, v, [&](int i) { return kb[i]; });
+        TL(8);
+    } else if (KM == KM_REGS2) {
         // its L2 round trip hides behind the exchange stage
         const cplx* __restrict__ g1 = bkp + P::M + t;
         asm volatile("" : "+l"(g1) : "d"(v[0].x), "d"(v[15].y));          // do not hoist the loads above the pass
@@ -182,7 +213,7 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
 template <typename Torus> struct StashWords { static constexpr int PER_C = 8 * (int)(sizeof(Torus) / 4); };   // words per c (4 complex)
 // PLAIN: the external product alone, ACC <- BK (x) ACC (tGswFFTExternMulToTLwe, cb/tgsw_functions.cpp:424-449): no rotation
 // on the way in, no accumulation on the way out.
-template <int LOGM, typename Torus, bool STASH, bool ALLREG, bool PLAIN = false>
+template <int LOGM, typename Torus, bool STASH, int KM, bool PLAIN = false>
 __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, const cplx* __restrict__ bk,
                                           const int l, const int Bgbit, cplx* __restrict__ buf, const uint32_t tacc,
                                           KeyPipe& kp, const cplx* __restrict__ tw, const int t, const int bar_id) {
@@ -202,7 +233,7 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
         const int sh = W - (lev + 1) * Bgbit;
         cplx v[16];
         TL(0);
-        if (!ALLREG && (t & 31) == 0) kp.poll();                 // keep the key stream moving (bk_pipe.cuh)
+        if (KM == KM_TMEM && (t & 31) == 0) kp.poll();                 // keep the key stream moving (bk_pipe.cuh)
         if (STASH && lev > 0) {
             uint32_t w[4][WPC];
 #pragma unroll
@@ -249,8 +280,8 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
             if (stash) tmem_wait_st();
         }
         TL(1);
-        if (p == 0) forward_and_mac<LOGM, true, ALLREG>(v, tacc, bk, buf, kp, tw, t, bar_id);
-        else        forward_and_mac<LOGM, false, ALLREG>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp, tw, t, bar_id);
+        if (p == 0) forward_and_mac<LOGM, true, KM>(v, tacc, bk, buf, kp, tw, t, bar_id);
+        else        forward_and_mac<LOGM, false, KM>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp, tw, t, bar_id);
     }
     // every lane has finished reading the accumulator once it passes the first sync inside tree_backward
     {
@@ -287,12 +318,12 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
 // Shared memory: twiddles | CTA control (KeyPipeShared, TMEM base) | key staging (KeyPipe only) | per group: transpose buffer, ACC
 // Tensor memory : per warp R0 (64 columns) | R1 (64) | stash (STASH only), warps of a lane quarter side by side; the key columns
 //                 of the KeyPipe configuration come after the last warp's window.
-template <int LOGM, typename Torus, int GROUPS, bool STASH, bool ALLREG> struct BRSmem {
+template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM> struct BRSmem {
     typedef TreePlan<LOGM> P;
     static constexpr size_t TW_BYTES = sizeof(cplx) * ((P::TW_TOTAL + 7) & ~7);        // 128-byte multiple
     static constexpr size_t CTRL_BYTES = 128;
     static constexpr size_t CHUNK_BYTES = sizeof(cplx) * 2 * P::M;                      // BK_i[p][0..1]
-    static constexpr size_t STAGE_BYTES = ALLREG ? 0 : CHUNK_BYTES;
+    static constexpr size_t STAGE_BYTES = KM == KM_TMEM ? CHUNK_BYTES : 0;
     static constexpr size_t BUF_BYTES = (sizeof(cplx) * P::BUF + 127) & ~(size_t)127;  // transpose buffer
     static constexpr size_t ACC_BYTES = sizeof(Torus) * 2 * P::N;
     static constexpr size_t GROUP_BYTES = BUF_BYTES + ACC_BYTES;
@@ -302,8 +333,8 @@ template <int LOGM, typename Torus, int GROUPS, bool STASH, bool ALLREG> struct 
     static_assert(TOTAL <= 232448, "shared memory budget (227 KB) exceeded");
     static constexpr int TMEM_COLS = 128 + (STASH ? 4 * StashWords<Torus>::PER_C : 0);
     static constexpr int KEY_COL = (WARPS + 3) / 4 * TMEM_COLS;
-    static_assert(KEY_COL + (ALLREG ? 0 : 128) <= 512, "tensor memory columns exceeded");
-    static_assert(ALLREG || P::T == 32, "KeyPipe: one warp per accumulator");
+    static_assert(KEY_COL + (KM == KM_TMEM ? 128 : 0) <= 512, "tensor memory columns exceeded");
+    static_assert(KM != KM_TMEM || P::T == 32, "KeyPipe: one warp per accumulator");
 };
 
 // rotation amount i of sample ct (i == n: the b part), straight from the kernel's inputs -- nothing is staged in shared memory
@@ -325,11 +356,11 @@ __device__ __forceinline__ int fetch_bara(const BRArgs& A, const int ct, const i
     return __ldg(A.bara + (size_t)ct * n + i);
 }
 
-template <int LOGM, typename Torus, int GROUPS, bool STASH, bool ALLREG>
+template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM>
 __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_kernel(const BRArgs A) {
     typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
-    typedef BRSmem<LOGM, Torus, GROUPS, STASH, ALLREG> S;
+    typedef BRSmem<LOGM, Torus, GROUPS, STASH, KM> S;
     constexpr int M = P::M, N = P::N, T = P::T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* tw = reinterpret_cast<cplx*>(smem_raw);
@@ -366,7 +397,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
     KeyPipe kp{kps, smem_raw + S::TW_BYTES + S::CTRL_BYTES, reinterpret_cast<const unsigned char*>(A.bkfft),
                tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)S::KEY_COL, tmem_base + (uint32_t)S::KEY_COL,
                (uint32_t)S::CHUNK_BYTES, (uint32_t)(A.n * 2 * A.l), 0u};
-    if (!ALLREG && threadIdx.x == 0) kp.prologue();
+    if (KM == KM_TMEM && threadIdx.x == 0) kp.prologue();
 
     if (unit < (long)A.count * n_mu) {                 // idle groups of the last CTA fall through to the final barrier
         const int ct = (int)(unit / n_mu), w = (int)(unit % n_mu);
@@ -406,10 +437,10 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
             const int a = a_next;
             if (i + 1 < n) a_next = fetch_bara<LOGM, Torus>(A, ct, i + 1);
             if (a == 0) {
-                if (!ALLREG) for (int p = 0; p < 2 * l; p++) { kp.acquire(t & 31); kp.release(t & 31); }     // stay aligned with the key stream
+                if (KM == KM_TMEM) for (int p = 0; p < 2 * l; p++) { kp.acquire(t & 31); kp.release(t & 31); }     // stay aligned with the key stream
                 continue;
             }
-            cmux_step<LOGM, Torus, STASH, ALLREG>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, kp, tw, t, bar_id);
+            cmux_step<LOGM, Torus, STASH, KM>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, kp, tw, t, bar_id);
         }
 
         TL(99);
@@ -442,7 +473,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
 template <int LOGM, typename Torus, int GROUPS>
 __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) extern_mul_kernel(const BRArgs A) {
     typedef TreePlan<LOGM> P;
-    typedef BRSmem<LOGM, Torus, GROUPS, true, true> S;
+    typedef BRSmem<LOGM, Torus, GROUPS, true, KM_REGS2> S;
     constexpr int N = P::N, T = P::T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* tw = reinterpret_cast<cplx*>(smem_raw);
@@ -468,7 +499,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) extern_mul_kern
         for (int j = t; j < 2 * N; j += T) acc[j] = io[j];
         lanes_sync<T>(bar_id);
         KeyPipe kp{};       // unused on the register-prefetch path
-        cmux_step<LOGM, Torus, true, true, true>(acc, 1, A.bkfft + (size_t)(unit / (A.units_per_gsw > 0 ? A.units_per_gsw : 1)) * A.bk_sample_stride, A.l, A.Bgbit, buf, tacc, kp, tw, t, bar_id);
+        cmux_step<LOGM, Torus, true, KM_REGS2, true>(acc, 1, A.bkfft + (size_t)(unit / (A.units_per_gsw > 0 ? A.units_per_gsw : 1)) * A.bk_sample_stride, A.l, A.Bgbit, buf, tacc, kp, tw, t, bar_id);
         for (int j = t; j < 2 * N; j += T) io[j] = acc[j];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -477,7 +508,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) extern_mul_kern
 }
 cudaError_t launch_extern_mul32(const BRArgs& a, cudaStream_t s) {
     constexpr int G = 8;
-    typedef BRSmem<9, int32_t, G, true, true> S;
+    typedef BRSmem<9, int32_t, G, true, KM_REGS2> S;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(extern_mul_kernel<9, int32_t, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
@@ -498,27 +529,30 @@ namespace tfhe_b200 {
 #endif
 static bool g_inited = false;
 // Configurations (profiles/r1_notes.md has the sweep):
-//   default:  8 warps per SM, key prefetched into registers, stash                    <9, int32,  8, true,  true>   172 k/s
-//   keytm  : 12 warps per SM, key through tensor memory (KeyPipe), no stash           <9, int32, 12, false, false>  163 k/s
+//   default:  8 warps per SM, key prefetched into registers, stash                    <9, int32,  8, true,  KM_REGS2> 174 k/s
+//   half   : 12 warps per SM, one key polynomial's worth of registers (KM_REGS1), stash <9, int32, 12, true,  KM_REGS1> 164 k/s
+//            (the LSU pipe, not the warp count, is the wall: 12 warps with the key through the LSU gain nothing over 8)
+//   keytm  : 12 warps per SM, key through tensor memory (KeyPipe), no stash           <9, int32, 12, false, KM_TMEM>  163 k/s
 //            (free-running 12 warps with the key "already there" measured 201 k/s; the CTA-wide lockstep on the single
 //             tensor-memory key buffer and the 2 200-cycle copy issue per chunk give that back -- kept selectable for round 2)
 constexpr int G32 = 8, G32_KP = 12, G64 = 4;     // accumulators per CTA (N=1024: one warp each; N=2048: two warps each)
 
-template <int LOGM, typename Torus, int GROUPS, bool STASH, bool ALLREG> static cudaError_t br_attr() {
-    return cudaFuncSetAttribute(blind_rotate_kernel<LOGM, Torus, GROUPS, STASH, ALLREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)BRSmem<LOGM, Torus, GROUPS, STASH, ALLREG>::TOTAL);
+template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM> static cudaError_t br_attr() {
+    return cudaFuncSetAttribute(blind_rotate_kernel<LOGM, Torus, GROUPS, STASH, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)BRSmem<LOGM, Torus, GROUPS, STASH, KM>::TOTAL);
 }
-template <int LOGM, typename Torus, int GROUPS, bool STASH, bool ALLREG> static cudaError_t br_launch(const BRArgs& a, long units, cudaStream_t s) {
+template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM> static cudaError_t br_launch(const BRArgs& a, long units, cudaStream_t s) {
     const int grid = (int)((units + GROUPS - 1) / GROUPS);
-    blind_rotate_kernel<LOGM, Torus, GROUPS, STASH, ALLREG><<<grid, GROUPS * TreePlan<LOGM>::T, BRSmem<LOGM, Torus, GROUPS, STASH, ALLREG>::TOTAL, s>>>(a);
+    blind_rotate_kernel<LOGM, Torus, GROUPS, STASH, KM><<<grid, GROUPS * TreePlan<LOGM>::T, BRSmem<LOGM, Torus, GROUPS, STASH, KM>::TOTAL, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t blind_rotate_init() {
     cudaError_t e;
-    if ((e = br_attr<9, int32_t, G32_KP, false, false>()) != cudaSuccess) return e;
-    if ((e = br_attr<9, int32_t, G32, true, true>()) != cudaSuccess) return e;
-    if ((e = br_attr<9, int32_t, G32, false, true>()) != cudaSuccess) return e;
-    if ((e = br_attr<10, int64_t, G64, false, true>()) != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, G32_KP, false, KM_TMEM>()) != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, G32_KP, true, KM_REGS1>()) != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, G32, true, KM_REGS2>()) != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, G32, false, KM_REGS2>()) != cudaSuccess) return e;
+    if ((e = br_attr<10, int64_t, G64, false, KM_REGS2>()) != cudaSuccess) return e;
     g_inited = true;
     return cudaSuccess;
 }
@@ -526,11 +560,12 @@ cudaError_t blind_rotate_init() {
 cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
     if (!g_inited) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
     if (a.count <= 0) return cudaSuccess;
-    // development knob: TFHE_B200_BR_VARIANT = keytm | nostash selects the measured alternatives
+    // development knob: TFHE_B200_BR_VARIANT = keytm | half | nostash selects the measured alternatives
     static const char* variant = getenv("TFHE_B200_BR_VARIANT");
-    if (variant && variant[0] == 'k') return br_launch<9, int32_t, G32_KP, false, false>(a, a.count, s);
-    if (variant && variant[0] == 'n') return br_launch<9, int32_t, G32, false, true>(a, a.count, s);
-    return br_launch<9, int32_t, G32, true, true>(a, a.count, s);
+    if (variant && variant[0] == 'k') return br_launch<9, int32_t, G32_KP, false, KM_TMEM>(a, a.count, s);
+    if (variant && variant[0] == 'h') return br_launch<9, int32_t, G32_KP, true, KM_REGS1>(a, a.count, s);
+    if (variant && variant[0] == 'n') return br_launch<9, int32_t, G32, false, KM_REGS2>(a, a.count, s);
+    return br_launch<9, int32_t, G32, true, KM_REGS2>(a, a.count, s);
 }
 cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
     if (!g_inited) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
@@ -538,7 +573,7 @@ cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
     const long units = (long)a.count * (a.n_mu > 0 ? a.n_mu : 1);
     // no stash for Torus64: 64 columns of u per lane cost more tensor-memory traffic than the re-reads save (232 vs 225 ms
     // per 4096 circuit bootstraps, profiles/r1_notes.md)
-    return br_launch<10, int64_t, G64, false, true>(a, units, s);
+    return br_launch<10, int64_t, G64, false, KM_REGS2>(a, units, s);
 }
 
 // ---------------------------------------------------------------------------------------------
