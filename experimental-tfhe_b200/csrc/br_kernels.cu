@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(256) poly_to_spectrum_kernel(cplx* __restrict_
                                                                const cplx* __restrict__ twg, int count, double scale) {
     typedef TreePlan<LOGM> P;
     constexpr int M = P::M, N = P::N, T = P::T;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* tw = reinterpret_cast<cplx*>(smem_raw);
     for (int i = threadIdx.x; i < P::TW_TOTAL; i += 256) tw[i] = twg[i];
     __syncthreads();
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(256) spectrum_to_torus_kernel(Torus* __restric
                                                                 const cplx* __restrict__ twg, int count, double scale) {
     typedef TreePlan<LOGM> P;
     constexpr int M = P::M, N = P::N, T = P::T;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx* tw = reinterpret_cast<cplx*>(smem_raw);
     for (int i = threadIdx.x; i < P::TW_TOTAL; i += 256) tw[i] = twg[i];
     __syncthreads();
@@ -632,7 +632,6 @@ __global__ void __launch_bounds__(256) spectrum_to_torus_kernel(Torus* __restric
     if (poly >= count) return;
     const cplx* src = in + (size_t)poly * M + t;
     cplx v[16];
-#pragma unroll
     const cplx* gf = twg + P::TG + t;
 #pragma unroll
     for (int i = 0; i < 16; i++) {          // 2/N pre-scale (:78-100), times the slot's unit factor g the backward tree expects
