@@ -102,6 +102,34 @@ int main() {
         ph = orc_lwePhase(out.data(), K->tlwe_key, gp.N);
         CHECK(abs(ph - MU) < (1 << 28), "tfhe_blindRotateAndExtract_FFT phase");
     }
+    {   // gate-level circuit: 6 instances of a 4-bit ripple-carry adder through tfhe_b200_circuit_eval_batch
+        const int bits = 4, B = 6, row = gp.n + 1;
+        AdderNetlist nl = ripple_carry_adder_netlist(bits);
+        std::vector<Torus32> wires((size_t)nl.n_wires * B * row, 0);
+        int xa[B] = {0, 15, 7, 9, 5, 12}, xb[B] = {0, 1, 8, 9, 10, 15}, xc[B] = {0, 1, 0, 1, 1, 0};
+        for (int k = 0; k < B; k++) {
+            for (int i = 0; i < bits; i++) {
+                orc_bootsSymEncrypt(&wires[((size_t)(nl.a0 + i) * B + k) * row], (xa[k] >> i) & 1, K, &r);
+                orc_bootsSymEncrypt(&wires[((size_t)(nl.b0 + i) * B + k) * row], (xb[k] >> i) & 1, K, &r);
+            }
+            orc_bootsSymEncrypt(&wires[((size_t)nl.cin * B + k) * row], xc[k], K, &r);
+        }
+        Torus32* d = nullptr;
+        cudaMalloc(&d, wires.size() * sizeof(Torus32));
+        cudaMemcpy(d, wires.data(), wires.size() * sizeof(Torus32), cudaMemcpyHostToDevice);
+        int rc = tfhe_b200_circuit_eval_batch(bkFFT.engine, nl.gates.data(), (int)nl.gates.size(), d, nl.n_wires, B, nullptr);
+        cudaDeviceSynchronize();
+        cudaMemcpy(wires.data(), d, wires.size() * sizeof(Torus32), cudaMemcpyDeviceToHost);
+        cudaFree(d);
+        int wrong = rc != 0;
+        for (int k = 0; k < B; k++) {
+            int sum = 0;
+            for (int i = 0; i < bits; i++) sum |= orc_bootsSymDecrypt(&wires[((size_t)(nl.s0 + i) * B + k) * row], K) << i;
+            sum |= orc_bootsSymDecrypt(&wires[((size_t)(nl.c0 + bits) * B + k) * row], K) << bits;
+            wrong += sum != xa[k] + xb[k] + xc[k];
+        }
+        CHECK(wrong == 0, "4-bit ripple-carry adders (ripple_carry_adder_netlist + tfhe_b200_circuit_eval_batch) add correctly");
+    }
     destroy_LweBootstrappingKeyFFT(&bkFFT);
     for (auto* p : bks) delete p;
     orc_gate_keys_free(K);
