@@ -139,11 +139,17 @@ enum { KM_REGS2 = 0, KM_TMEM = 1, KM_REGS1 = 2 };
 template <int LOGM, bool FIRST, int KM>
 __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t tacc, const cplx* __restrict__ bkp,
                                                 cplx* __restrict__ buf, KeyPipe& kp,
-                                                const cplx* __restrict__ tw, const int t, const int bar_id) {
+                                                const cplx* __restrict__ tw, const int t, const int bar_id, const uint32_t ttw) {
     typedef TreePlan<LOGM> P;
-    tree_forward_a<LOGM>(v, buf, tw, t, bar_id);
-    if (KM == KM_TMEM && (t & 31) == 0) kp.poll();
-    tree_forward_b<LOGM>(v, tw, t);
+    if constexpr (KM == KM_REGS2) {
+        Tw8Regs q;
+        tree_forward_a<LOGM>(v, buf, tw, t, bar_id, [&]() { tw8_issue(q, ttw); });      // depths 4-7 twiddles ride behind the transpose
+        tree_forward_b_tm(v, q);
+    } else {
+        tree_forward_a<LOGM>(v, buf, tw, t, bar_id);
+        if (KM == KM_TMEM && (t & 31) == 0) kp.poll();
+        tree_forward_b<LOGM>(v, tw, t);
+    }
     TL(4);
     if (KM == KM_REGS1) {
         const cplx* __restrict__ g0 = bkp + t;
@@ -151,7 +157,7 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
         cplx kb[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) kb[i] = __ldg(g0 + i * P::T);
-        tree_forward_c<LOGM>(v, tw, t);
+        tree_forward_c<LOGM, KM == KM_REGS2>(v, tw, t, ttw);
         TL(6);
         // R0 += v * BK[p][0]; each consumed chunk's registers are refilled with the same slots of BK[p][1]
 #pragma unroll
@@ -183,7 +189,7 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
 #pragma unroll
         for (int i = 0; i < 16; i++) b0r[i] = __ldg(g1 - P::M + i * P::T);
         TL(5);
-        tree_forward_c<LOGM>(v, tw, t);
+        tree_forward_c<LOGM, KM == KM_REGS2>(v, tw, t, ttw);
         TL(6);
         // (a software-pipelined variant, next chunk's tcgen05.ld in flight during the FMAs, was 5 % slower: profiles/r1_notes.md)
         mac_tmem<FIRST>(tacc, v, [&](int i) { return b0r[i]; });
@@ -191,7 +197,7 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
         mac_tmem<FIRST>(tacc + 64, v, [&](int i) { return b1[i]; });
         TL(8);
     } else {
-        tree_forward_c<LOGM>(v, tw, t);
+        tree_forward_c<LOGM, KM == KM_REGS2>(v, tw, t, ttw);
         TL(6);
         kp.acquire(t & 31);
         TL(16);
@@ -216,7 +222,7 @@ template <typename Torus> struct StashWords { static constexpr int PER_C = 8 * (
 template <int LOGM, typename Torus, bool STASH, int KM, bool PLAIN = false>
 __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, const cplx* __restrict__ bk,
                                           const int l, const int Bgbit, cplx* __restrict__ buf, const uint32_t tacc,
-                                          KeyPipe& kp, const cplx* __restrict__ tw, const int t, const int bar_id) {
+                                          KeyPipe& kp, const cplx* __restrict__ tw, const int t, const int bar_id, const uint32_t ttw = 0) {
     typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
     constexpr int M = P::M, N = P::N, T = P::T, W = TorusTraits<Torus>::W;
@@ -280,8 +286,8 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
             if (stash) tmem_wait_st();
         }
         TL(1);
-        if (p == 0) forward_and_mac<LOGM, true, KM>(v, tacc, bk, buf, kp, tw, t, bar_id);
-        else        forward_and_mac<LOGM, false, KM>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp, tw, t, bar_id);
+        if (p == 0) forward_and_mac<LOGM, true, KM>(v, tacc, bk, buf, kp, tw, t, bar_id, ttw);
+        else        forward_and_mac<LOGM, false, KM>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp, tw, t, bar_id, ttw);
     }
     // every lane has finished reading the accumulator once it passes the first sync inside tree_backward
     {
@@ -289,7 +295,7 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
         TL(0);
         load_tmem(R, tacc);
         TL(9);
-        tree_backward<LOGM>(R, buf, tw, t, bar_id);
+        tree_backward<LOGM, KM == KM_REGS2>(R, buf, tw, t, bar_id, ttw);
 #pragma unroll
         for (int m = 0; m < 16; m++) {
             const int j = t + T * m;
@@ -302,7 +308,7 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
         cplx R[16];
         load_tmem(R, tacc + 64);
         TL(9);
-        tree_backward<LOGM>(R, buf, tw, t, bar_id);
+        tree_backward<LOGM, KM == KM_REGS2>(R, buf, tw, t, bar_id, ttw);
 #pragma unroll
         for (int m = 0; m < 16; m++) {
             const int j = t + T * m;
@@ -331,7 +337,9 @@ template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM> struct BRSme
     static constexpr size_t TOTAL = GROUPS_OFF + GROUPS * GROUP_BYTES;
     static constexpr int WARPS = GROUPS * P::T / 32;
     static_assert(TOTAL <= 232448, "shared memory budget (227 KB) exceeded");
-    static constexpr int TMEM_COLS = 128 + (STASH ? 4 * StashWords<Torus>::PER_C : 0);
+    static constexpr bool TWT = KM == KM_REGS2;                                         // per-lane twiddles in tensor memory (tree_fft.cuh)
+    static constexpr int TW_COL = 128 + (STASH ? 4 * StashWords<Torus>::PER_C : 0);
+    static constexpr int TMEM_COLS = TW_COL + (TWT ? 32 * (2 + (P::NS > 1 ? 1 : 0)) : 0);
     static constexpr int KEY_COL = (WARPS + 3) / 4 * TMEM_COLS;
     static_assert(KEY_COL + (KM == KM_TMEM ? 128 : 0) <= 512, "tensor memory columns exceeded");
     static_assert(KM != KM_TMEM || P::T == 32, "KeyPipe: one warp per accumulator");
@@ -394,6 +402,8 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_base_slot;
     const uint32_t tacc = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)S::TMEM_COLS;   // R0 | R1 | stash
+    const uint32_t ttw = S::TWT ? tacc + (uint32_t)S::TW_COL : 0u;
+    if (S::TWT) tree_twiddles_to_tmem<LOGM>(tw, t, ttw);
     KeyPipe kp{kps, smem_raw + S::TW_BYTES + S::CTRL_BYTES, reinterpret_cast<const unsigned char*>(A.bkfft),
                tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)S::KEY_COL, tmem_base + (uint32_t)S::KEY_COL,
                (uint32_t)S::CHUNK_BYTES, (uint32_t)(A.n * 2 * A.l), 0u};
@@ -440,7 +450,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
                 if (KM == KM_TMEM) for (int p = 0; p < 2 * l; p++) { kp.acquire(t & 31); kp.release(t & 31); }     // stay aligned with the key stream
                 continue;
             }
-            cmux_step<LOGM, Torus, STASH, KM>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, kp, tw, t, bar_id);
+            cmux_step<LOGM, Torus, STASH, KM>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, kp, tw, t, bar_id, ttw);
         }
 
         TL(99);
@@ -499,7 +509,9 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) extern_mul_kern
         for (int j = t; j < 2 * N; j += T) acc[j] = io[j];
         lanes_sync<T>(bar_id);
         KeyPipe kp{};       // unused on the register-prefetch path
-        cmux_step<LOGM, Torus, true, KM_REGS2, true>(acc, 1, A.bkfft + (size_t)(unit / (A.units_per_gsw > 0 ? A.units_per_gsw : 1)) * A.bk_sample_stride, A.l, A.Bgbit, buf, tacc, kp, tw, t, bar_id);
+        const uint32_t ttw = tacc + (uint32_t)S::TW_COL;
+        tree_twiddles_to_tmem<LOGM>(tw, t, ttw);
+        cmux_step<LOGM, Torus, true, KM_REGS2, true>(acc, 1, A.bkfft + (size_t)(unit / (A.units_per_gsw > 0 ? A.units_per_gsw : 1)) * A.bk_sample_stride, A.l, A.Bgbit, buf, tacc, kp, tw, t, bar_id, ttw);
         for (int j = t; j < 2 * N; j += T) io[j] = acc[j];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

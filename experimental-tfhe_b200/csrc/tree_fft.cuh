@@ -140,6 +140,51 @@ template <int T> __device__ __forceinline__ void lanes_sync(int bar_id) {
     else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-lane twiddles from TENSOR MEMORY (blind-rotation kernel, 8-warp configurations).  The 16 (N=1024) / 24 (N=2048) twiddles a
+// lane needs after the transpose are lane-specific, so they cannot come from the constant bank; read from shared memory they are
+// 16-24 LDS.128 per transform = 14 % of the kernel's LSU wavefronts, and the LSU pipe is its busiest unit (66 %).  Each lane keeps
+// them in 64 / 96 of its tensor-memory columns instead: [0,32) depths 4-7 (its TB row), [32,64) depth 8, [64,96) depth 9.
+// tcgen05.ld has its own datapath.  ttw = 0 selects the shared-memory path (standalone transforms, 12-warp variants).
+// ---------------------------------------------------------------------------------------------
+#define TREE_TLD16(r, addr)                                                                                                    \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"       \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                     \
+                 : "r"(addr) : "memory")
+#define TREE_TST16(r, addr)                                                                                                    \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"       \
+                 ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), \
+                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(addr) : "memory")
+// eight twiddles (32 columns at taddr) -> registers, in two halves so that the tensor-memory latency can hide behind whatever
+// the caller does between issue and collect (a transpose read, a lane exchange)
+struct Tw8Regs { uint32_t r0[16], r1[16]; };
+__device__ __forceinline__ void tw8_issue(Tw8Regs& q, const uint32_t taddr) {
+    TREE_TLD16(q.r0, taddr);
+    TREE_TLD16(q.r1, taddr + 16);
+}
+__device__ __forceinline__ void tw8_collect(cplx (&E)[8], const Tw8Regs& q) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const uint32_t (&r0)[16] = q.r0; const uint32_t (&r1)[16] = q.r1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        E[i] = make_double2(__hiloint2double((int)r0[4 * i + 1], (int)r0[4 * i]), __hiloint2double((int)r0[4 * i + 3], (int)r0[4 * i + 2]));
+        E[4 + i] = make_double2(__hiloint2double((int)r1[4 * i + 1], (int)r1[4 * i]), __hiloint2double((int)r1[4 * i + 3], (int)r1[4 * i + 2]));
+    }
+}
+__device__ __forceinline__ void tw8_to_tmem(const cplx (&E)[8], const uint32_t taddr) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            r[4 * i] = (uint32_t)__double2loint(E[4 * h + i].x); r[4 * i + 1] = (uint32_t)__double2hiint(E[4 * h + i].x);
+            r[4 * i + 2] = (uint32_t)__double2loint(E[4 * h + i].y); r[4 * i + 3] = (uint32_t)__double2hiint(E[4 * h + i].y);
+        }
+        TREE_TST16(r, taddr + 16 * h);
+    }
+}
+
 // four tree depths on the 16 registers of a lane; E = the 8 essential twiddles of these depths
 template <bool INV> __device__ __forceinline__ void pass16(cplx (&v)[16], const cplx* __restrict__ E, const int estride) {
     if (!INV) {
@@ -197,8 +242,10 @@ template <int LOGM> __device__ __forceinline__ int tree_side(const int t) {     
 // Forward: in  v[m] = z_{t + T m}  (t = lane in [0,T), natural coefficient order, stride T)
 //          out v[i] = spectrum slot i of this lane (leaf order, private)
 // Split in two so the caller can reuse the transpose buffer between the halves (after part A nobody reads buf any more).
-template <int LOGM>
-__device__ __forceinline__ void tree_forward_a(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id) {
+struct TreeNoHook { __device__ __forceinline__ void operator()() const {} };
+template <int LOGM, typename Hook = TreeNoHook>
+__device__ __forceinline__ void tree_forward_a(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id,
+                                               Hook mid = Hook()) {
     typedef TreePlan<LOGM> P;
     constexpr int T = P::T;
     pass16<false>(v, reinterpret_cast<const cplx*>(c_tree_ta), 1);
@@ -206,6 +253,7 @@ __device__ __forceinline__ void tree_forward_a(cplx (&v)[16], cplx* __restrict__
     lanes_sync<T>(bar_id);                                   // WAR: earlier reads of buf
 #pragma unroll
     for (int m = 0; m < 16; m++) buf[m * P::S + t] = v[m];
+    mid();                                                   // v is dead here: room to start something long (twiddle loads)
     lanes_sync<T>(bar_id);
     const int b = t / P::P, p = t % P::P;
 #pragma unroll
@@ -213,26 +261,67 @@ __device__ __forceinline__ void tree_forward_a(cplx (&v)[16], cplx* __restrict__
     lanes_sync<T>(bar_id);                                   // every lane is done with buf
     TL(3);
 }
+// this lane's post-transpose twiddles -> its tensor-memory columns at ttw (once per kernel)
+template <int LOGM>
+__device__ __forceinline__ void tree_twiddles_to_tmem(const cplx* __restrict__ tw, const int t, const uint32_t ttw) {
+    typedef TreePlan<LOGM> P;
+    cplx E[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) E[e] = tw[P::TB + tree_side<LOGM>(t) * 128 + e * 16 + t / P::P];
+    tw8_to_tmem(E, ttw);
+#pragma unroll
+    for (int m = 0; m < 8; m++) E[m] = tw[P::TC0 + m * P::T + t];
+    tw8_to_tmem(E, ttw + 32);
+    if (P::NS > 1) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) E[m] = tw[P::TC1 + m * P::T + t];
+        tw8_to_tmem(E, ttw + 64);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 template <int LOGM>
 __device__ __forceinline__ void tree_forward_b(cplx (&v)[16], const cplx* __restrict__ tw, const int t) {      // depths 4-7
     typedef TreePlan<LOGM> P;
     pass16<false>(v, tw + P::TB + tree_side<LOGM>(t) * 128 + t / P::P, 16);
 }
-template <int LOGM>
-__device__ __forceinline__ void tree_forward_c(cplx (&v)[16], const cplx* __restrict__ tw, const int t) {      // depths 8..
+// same with the twiddles already on their way from tensor memory (tw8_issue(q, ttw) before the transpose read)
+__device__ __forceinline__ void tree_forward_b_tm(cplx (&v)[16], const Tw8Regs& q) {
+    cplx E[8];
+    tw8_collect(E, q);
+    pass16<false>(v, E, 1);
+}
+template <int LOGM, bool TT = false>
+__device__ __forceinline__ void tree_forward_c(cplx (&v)[16], const cplx* __restrict__ tw, const int t, const uint32_t ttw = 0) {      // depths 8..
     typedef TreePlan<LOGM> P;
     constexpr int T = P::T;
     {   // depth 8
-        odd_swap(v, P::P >> 1);
-        const cplx* e = tw + P::TC0 + t;
+        if constexpr (TT) {
+            // (issued only now: the caller holds 128 registers of key values in flight across this stage)
+            odd_swap(v, P::P >> 1);
+            Tw8Regs q; tw8_issue(q, ttw + 32);
+            cplx E[8]; tw8_collect(E, q);
 #pragma unroll
-        for (int m = 0; m < 8; m++) bf_fwd(v[2 * m], v[2 * m + 1], e[m * T]);
+            for (int m = 0; m < 8; m++) bf_fwd(v[2 * m], v[2 * m + 1], E[m]);
+        } else {
+            odd_swap(v, P::P >> 1);
+            const cplx* e = tw + P::TC0 + t;
+#pragma unroll
+            for (int m = 0; m < 8; m++) bf_fwd(v[2 * m], v[2 * m + 1], e[m * T]);
+        }
     }
     if (P::NS > 1) {   // depth 9 (M = 1024)
-        odd_swap(v, 1);
-        const cplx* e = tw + P::TC1 + t;
+        if constexpr (TT) {
+            odd_swap(v, 1);
+            Tw8Regs q; tw8_issue(q, ttw + 64);
+            cplx E[8]; tw8_collect(E, q);
 #pragma unroll
-        for (int m = 0; m < 8; m++) bf_fwd(v[2 * m], v[2 * m + 1], e[m * T]);
+            for (int m = 0; m < 8; m++) bf_fwd(v[2 * m], v[2 * m + 1], E[m]);
+        } else {
+            odd_swap(v, 1);
+            const cplx* e = tw + P::TC1 + t;
+#pragma unroll
+            for (int m = 0; m < 8; m++) bf_fwd(v[2 * m], v[2 * m + 1], e[m * T]);
+        }
     }
 }
 template <int LOGM>
@@ -243,25 +332,43 @@ __device__ __forceinline__ void tree_forward(cplx (&v)[16], cplx* __restrict__ b
 }
 
 // Backward: the exact mirror.  in v[i] = spectrum slot i (times g) ; out v[m] = M * z_{t + T m}
-template <int LOGM>
-__device__ __forceinline__ void tree_backward(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id) {
+template <int LOGM, bool TT = false>
+__device__ __forceinline__ void tree_backward(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id,
+                                              const uint32_t ttw = 0) {
     typedef TreePlan<LOGM> P;
     constexpr int T = P::T;
     const int b = t / P::P, p = t % P::P;
+    Tw8Regs qn;                                             // the next stage's twiddles, loaded one stage ahead
     if (P::NS > 1) {
-        const cplx* e = tw + P::TC1 + t;
+        if constexpr (TT) {
+            Tw8Regs q; tw8_issue(q, ttw + 64); tw8_issue(qn, ttw + 32);
+            cplx E[8]; tw8_collect(E, q);
 #pragma unroll
-        for (int m = 0; m < 8; m++) bf_inv(v[2 * m], v[2 * m + 1], e[m * T]);
+            for (int m = 0; m < 8; m++) bf_inv(v[2 * m], v[2 * m + 1], E[m]);
+        } else {
+            const cplx* e = tw + P::TC1 + t;
+#pragma unroll
+            for (int m = 0; m < 8; m++) bf_inv(v[2 * m], v[2 * m + 1], e[m * T]);
+        }
         odd_swap(v, 1);
     }
     {
-        const cplx* e = tw + P::TC0 + t;
+        if constexpr (TT) {
+            if (P::NS == 1) tw8_issue(qn, ttw + 32);
+            cplx E[8]; tw8_collect(E, qn);
+            tw8_issue(qn, ttw);                              // depths 7-4, collected after the exchange
 #pragma unroll
-        for (int m = 0; m < 8; m++) bf_inv(v[2 * m], v[2 * m + 1], e[m * T]);
+            for (int m = 0; m < 8; m++) bf_inv(v[2 * m], v[2 * m + 1], E[m]);
+        } else {
+            const cplx* e = tw + P::TC0 + t;
+#pragma unroll
+            for (int m = 0; m < 8; m++) bf_inv(v[2 * m], v[2 * m + 1], e[m * T]);
+        }
         odd_swap(v, P::P >> 1);
     }
     TL(10);
-    pass16<true>(v, tw + P::TB + tree_side<LOGM>(t) * 128 + b, 16);
+    if constexpr (TT) { cplx E[8]; tw8_collect(E, qn); pass16<true>(v, E, 1); }
+    else pass16<true>(v, tw + P::TB + tree_side<LOGM>(t) * 128 + b, 16);
     TL(11);
     lanes_sync<T>(bar_id);
 #pragma unroll
