@@ -79,8 +79,12 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 // R (in TMEM at taddr, 64 columns) (+)= v (.) b over this lane's 16 spectrum slots; FIRST: plain product, nothing to load.
 // b(i) yields the key value of slot i (shared memory or registers).
+// Ordering rule used throughout: a tcgen05.ld of columns this thread has stored needs tcgen05.wait::st in between.  The wait sits
+// in front of the LOADS (here, load_tmem, the stash reload), not behind the stores, so a store's latency overlaps with whatever
+// comes next (the following decomposition and transform) instead of being waited out on the spot.
 template <bool FIRST, typename BFn>
 __device__ __forceinline__ void mac_tmem(const uint32_t taddr, const cplx (&v)[16], BFn b) {
+    if (!FIRST) tmem_wait_st();
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         uint32_t r[16];
@@ -95,11 +99,11 @@ __device__ __forceinline__ void mac_tmem(const uint32_t taddr, const cplx (&v)[1
         }
         TFHE_TST16(r, taddr + 16 * c);
     }
-    tmem_wait_st();
 }
 // same, key values from tensor memory (KeyPipe): kaddr = the 64 key columns of this polynomial
 template <bool FIRST>
 __device__ __forceinline__ void mac_tmem_keytm(const uint32_t taddr, const uint32_t kaddr, const cplx (&v)[16]) {
+    if (!FIRST) tmem_wait_st();
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         uint32_t r[16], kq[16];
@@ -119,14 +123,16 @@ __device__ __forceinline__ void mac_tmem_keytm(const uint32_t taddr, const uint3
     }
 }
 __device__ __forceinline__ void load_tmem(cplx (&R)[16], const uint32_t taddr) {
+    uint32_t r[4][16];
+    tmem_wait_st();
+#pragma unroll
+    for (int c = 0; c < 4; c++) TFHE_TLD16(r[c], taddr + 16 * c);          // all four in flight, one wait
+    tmem_wait_ld();
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        uint32_t r[16];
-        TFHE_TLD16(r, taddr + 16 * c);
-        tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 4; i++)
-            R[4 * c + i] = make_double2(__hiloint2double((int)r[4 * i + 1], (int)r[4 * i]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]));
+            R[4 * c + i] = make_double2(__hiloint2double((int)r[c][4 * i + 1], (int)r[c][4 * i]), __hiloint2double((int)r[c][4 * i + 3], (int)r[c][4 * i + 2]));
     }
 }
 
@@ -207,8 +213,6 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
         TL(8);
         kp.release(t & 31);              // the key loads of both polynomials have been waited for
         TL(17);
-        tmem_wait_st();
-        TL(18);
     }
 }
 
@@ -242,6 +246,7 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
         if (KM == KM_TMEM && (t & 31) == 0) kp.poll();                 // keep the key stream moving (bk_pipe.cuh)
         if (STASH && lev > 0) {
             uint32_t w[4][WPC];
+            tmem_wait_st();
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 if constexpr (WPC == 8) { TFHE_TLD8(w[c], tacc + 128 + WPC * c); }
@@ -283,7 +288,7 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
                     else                    { TFHE_TST16(w, tacc + 128 + WPC * c); }
                 }
             }
-            if (stash) tmem_wait_st();
+            // (no wait::st here: the reload at the next level waits)
         }
         TL(1);
         if (p == 0) forward_and_mac<LOGM, true, KM>(v, tacc, bk, buf, kp, tw, t, bar_id, ttw);
