@@ -197,7 +197,8 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
         TL(5);
         tree_forward_c<LOGM, KM == KM_REGS2>(v, tw, t, ttw);
         TL(6);
-        // (a software-pipelined variant, next chunk's tcgen05.ld in flight during the FMAs, was 5 % slower: profiles/r1_notes.md)
+        // (loading both accumulators' chunks together, or the next chunk during the FMAs, was 5 % slower each time: the compiler
+        //  overlaps the depth-8 butterflies with this loop as it stands -- profiles/r1_notes.md)
         mac_tmem<FIRST>(tacc, v, [&](int i) { return b0r[i]; });
         TL(7);
         mac_tmem<FIRST>(tacc + 64, v, [&](int i) { return b1[i]; });
