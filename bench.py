@@ -114,6 +114,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# stdout carries exactly ONE JSON line.  Libraries write banners to file descriptor 1 behind Python's back (NCCL prints
+# "NCCL version ..." there when NCCL_DEBUG is set in the environment), so fd 1 is pointed at stderr for the whole run and
+# the result line goes to a private duplicate of the original stdout.
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -134,7 +157,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "gates/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -147,6 +170,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="gates per GPU per step (default: the BASELINE configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _guard_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -165,8 +189,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner/debug output (NCCL_DEBUG=VERSION|INFO in the environment) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     eng = mod.Engine(local)
 
@@ -277,7 +299,7 @@ def main():
             threads = host_threads()
             rate, kind, sample = cpu_gate_rate(threads * 256, threads)
             line["cpu_baseline"] = {"value": rate, "unit": "gates/s", "cores": threads, "kind": kind, "sample": sample}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
