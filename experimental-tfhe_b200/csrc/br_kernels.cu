@@ -122,6 +122,22 @@ __device__ __forceinline__ void mac_tmem_keytm(const uint32_t taddr, const uint3
         TFHE_TST16(r, taddr + 16 * c);
     }
 }
+// both accumulators (128 columns) with eight loads in flight
+__device__ __forceinline__ void load_tmem2(cplx (&R0)[16], cplx (&R1)[16], const uint32_t taddr) {
+    uint32_t r[8][16];
+    tmem_wait_st();
+#pragma unroll
+    for (int c = 0; c < 8; c++) TFHE_TLD16(r[c], taddr + 16 * c);
+    tmem_wait_ld();
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            R0[4 * c + i] = make_double2(__hiloint2double((int)r[c][4 * i + 1], (int)r[c][4 * i]), __hiloint2double((int)r[c][4 * i + 3], (int)r[c][4 * i + 2]));
+            R1[4 * c + i] = make_double2(__hiloint2double((int)r[4 + c][4 * i + 1], (int)r[4 + c][4 * i]), __hiloint2double((int)r[4 + c][4 * i + 3], (int)r[4 + c][4 * i + 2]));
+        }
+    }
+}
 __device__ __forceinline__ void load_tmem(cplx (&R)[16], const uint32_t taddr) {
     uint32_t r[4][16];
     tmem_wait_st();
@@ -295,7 +311,24 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
         if (p == 0) forward_and_mac<LOGM, true, KM>(v, tacc, bk, buf, kp, tw, t, bar_id, ttw);
         else        forward_and_mac<LOGM, false, KM>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp, tw, t, bar_id, ttw);
     }
-    // every lane has finished reading the accumulator once it passes the first sync inside tree_backward
+    // every lane has finished reading the accumulator once it passes the first sync inside the backward transform
+    if constexpr (KM == KM_REGS2 && sizeof(Torus) == 4) {
+        // both polynomials together: no key values are in flight here, so there is room for two data sets (tree_fft.cuh)
+        cplx R0[16], R1[16];
+        TL(0);
+        load_tmem2(R0, R1, tacc);
+        TL(9);
+        tree_backward2<LOGM, true>(R0, R1, buf, tw, t, bar_id, ttw);
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const int j = t + T * m;
+            acc[j] = (Torus)((PLAIN ? (U)0 : (U)acc[j]) + (U)to_torus(R0[m].x, (Torus)0));
+            acc[j + M] = (Torus)((PLAIN ? (U)0 : (U)acc[j + M]) + (U)to_torus(R0[m].y, (Torus)0));
+            acc[N + j] = (Torus)((PLAIN ? (U)0 : (U)acc[N + j]) + (U)to_torus(R1[m].x, (Torus)0));
+            acc[N + j + M] = (Torus)((PLAIN ? (U)0 : (U)acc[N + j + M]) + (U)to_torus(R1[m].y, (Torus)0));
+        }
+        TL(14);
+    } else {
     {
         cplx R[16];
         TL(0);
@@ -322,6 +355,7 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
             acc[N + j + M] = (Torus)((PLAIN ? (U)0 : (U)acc[N + j + M]) + (U)to_torus(R[m].y, (Torus)0));
         }
         TL(14);
+    }
     }
     lanes_sync<T>(bar_id);      // accumulator writes visible before the next step's rotated reads
     TL(15);

@@ -381,6 +381,68 @@ __device__ __forceinline__ void tree_backward(cplx (&v)[16], cplx* __restrict__ 
     TL(13);
 }
 
+// Two backward transforms side by side (the two polynomials of a TLWE accumulator): the stages are interleaved so each
+// latency-bound step (twiddle fetch, lane exchange, transpose) is paid once for two independent data sets, and the twiddles are
+// fetched once.  Uses the one transpose buffer twice.  Needs 128 data registers: only where no key values are in flight.
+template <int LOGM, bool TT = false>
+__device__ __forceinline__ void tree_backward2(cplx (&v)[16], cplx (&u)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t,
+                                               const int bar_id, const uint32_t ttw = 0) {
+    typedef TreePlan<LOGM> P;
+    constexpr int T = P::T;
+    const int b = t / P::P, p = t % P::P;
+    Tw8Regs qn;
+    if (P::NS > 1) {
+        cplx E[8];
+        if constexpr (TT) { Tw8Regs q; tw8_issue(q, ttw + 64); tw8_issue(qn, ttw + 32); tw8_collect(E, q); }
+        else {
+#pragma unroll
+            for (int m = 0; m < 8; m++) E[m] = tw[P::TC1 + m * T + t];
+        }
+#pragma unroll
+        for (int m = 0; m < 8; m++) { bf_inv(v[2 * m], v[2 * m + 1], E[m]); bf_inv(u[2 * m], u[2 * m + 1], E[m]); }
+        odd_swap(v, 1); odd_swap(u, 1);
+    }
+    {
+        cplx E[8];
+        if constexpr (TT) { if (P::NS == 1) tw8_issue(qn, ttw + 32); tw8_collect(E, qn); tw8_issue(qn, ttw); }
+        else {
+#pragma unroll
+            for (int m = 0; m < 8; m++) E[m] = tw[P::TC0 + m * T + t];
+        }
+#pragma unroll
+        for (int m = 0; m < 8; m++) { bf_inv(v[2 * m], v[2 * m + 1], E[m]); bf_inv(u[2 * m], u[2 * m + 1], E[m]); }
+        odd_swap(v, P::P >> 1); odd_swap(u, P::P >> 1);
+    }
+    TL(10);
+    {
+        cplx E[8];
+        if constexpr (TT) tw8_collect(E, qn);
+        else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) E[e] = tw[P::TB + tree_side<LOGM>(t) * 128 + e * 16 + b];
+        }
+        pass16<true>(v, E, 1);
+        pass16<true>(u, E, 1);
+    }
+    TL(11);
+    lanes_sync<T>(bar_id);
+#pragma unroll
+    for (int k = 0; k < 16; k++) buf[b * P::S + p + P::P * k] = v[k];
+    lanes_sync<T>(bar_id);
+#pragma unroll
+    for (int m = 0; m < 16; m++) v[m] = buf[m * P::S + t];
+    lanes_sync<T>(bar_id);                                   // everybody has read the first polynomial
+#pragma unroll
+    for (int k = 0; k < 16; k++) buf[b * P::S + p + P::P * k] = u[k];
+    lanes_sync<T>(bar_id);
+#pragma unroll
+    for (int m = 0; m < 16; m++) u[m] = buf[m * P::S + t];
+    TL(12);
+    pass16<true>(v, reinterpret_cast<const cplx*>(c_tree_ta), 1);
+    pass16<true>(u, reinterpret_cast<const cplx*>(c_tree_ta), 1);
+    TL(13);
+}
+
 // ---------------------------------------------------------------------------------------------
 // double -> torus, truncation toward zero then wrap, on the FP64 pipe (F2I is full rate there; the
 // integer bit-twiddling form costs ~25 ALU ops, see profiles/microbench_r1.txt).
