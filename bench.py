@@ -152,7 +152,7 @@ def run_reference(args):
     value = sum(rates) / len(rates)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "gates/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic (uniform random ciphertexts; keys from the oracle's key generator, seed 42)",
             "config": {"workload": WORKLOAD, "cpu_sample_per_step": per_step},
             "cpu_baseline": {"value": value, "unit": "gates/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -179,7 +179,6 @@ def main():
     import torch.distributed as dist
     mod = importlib.import_module("experimental-tfhe_b200")
     par = importlib.import_module("experimental-tfhe_b200.parallel")
-    import oracle_lib as O     # key generation only (client side, out of the hot path's scope): never in the timed region
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -192,13 +191,18 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     eng = mod.Engine(local)
 
-    # keys: generated once on rank 0's host (oracle keygen, seed 42), transformed on its GPU, replicated by NCCL broadcast
+    # keys: synthetic key material of the P_gate shapes (uniform random torus values, seed 42 -- key generation is client side and
+    # out of scope, and the oracle is not used on this arm; timing does not depend on the values: a real key's polynomials are
+    # uniform too).  Generated on rank 0's host, transformed on its GPU, replicated by NCCL broadcast.
     B = args.batch
-    g = O.GateOracle(42) if rank == 0 else None
-    params = g.engine_params() if rank == 0 else None
-    if world > 1:
-        obj = [params]; dist.broadcast_object_list(obj, src=0); params = obj[0]
-    par.replicate_gate_keys(eng, params, g.bk if g else None, g.ks if g else None, device=dev)
+    params = dict(n=500, N=1024, k=1, bk_l=2, bk_Bgbit=10, ks_t=8, ks_basebit=2)
+    bk_host = ks_host = None
+    if rank == 0:
+        krng = np.random.default_rng(42)
+        bk_host = krng.integers(-2**31, 2**31 - 1, size=(params["n"], 2 * params["bk_l"], 2, params["N"]), dtype=np.int64).astype(np.int32)
+        ks_host = krng.integers(-2**31, 2**31 - 1, size=(params["N"], params["ks_t"], 1 << params["ks_basebit"], params["n"] + 1),
+                                dtype=np.int64).astype(np.int32)
+    par.replicate_gate_keys(eng, params, bk_host, ks_host, device=dev)
     n = params["n"]
 
     # synthetic ciphertexts: i.i.d. uniform int32 (timing is data independent), distinct per rank
@@ -278,7 +282,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64", "data": "synthetic (uniform random ciphertexts and key material of the P_gate shapes)",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "parallelism": f"batch-sharded x{world}, keys replicated",
                        "l2": "inputs+outputs per step (393 MB + 268 MB scratch) exceed the 126 MB L2; no explicit flush"},
             "e2e": {"value": gates / t_e2e, "unit": "gates/s", "h2d_bytes_per_step": 2 * B * (n + 1) * 4, "d2h_bytes_per_step": B * (n + 1) * 4,

@@ -114,7 +114,7 @@ __device__ __constant__ double c_tree_ta[16] = {
     0x1.294062ed59f06p-2, 0x1.e9f4156c62ddap-1,   // w(3,6)
 };
 
-// Development instrumentation (tools/br_timeline.py builds a private library with -DBR_TIMELINE): per-warp cycle counts
+// Development instrumentation (tests/dev/br_timeline.py builds a private library with -DBR_TIMELINE): per-warp cycle counts
 // between marks, accumulated by lane 0.  Compiles to nothing in the product build.
 #ifdef BR_TIMELINE
 __device__ long long g_tl_acc[32 * 32];

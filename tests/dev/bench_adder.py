@@ -1,7 +1,7 @@
 """BASELINE configs[2]: batch of 32-bit ripple-carry adders through tfhe_b200_circuit_eval_batch (development timing tool).
-Usage: python tools/bench_adder.py [adders]      prints adders/s and gates/s, checks every decrypted sum."""
+Usage: python tests/dev/bench_adder.py [adders]      prints adders/s and gates/s, checks every decrypted sum."""
 import importlib, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 import oracle_lib as O

@@ -4,7 +4,7 @@ config 4: 4,096 tfhe_CircuitBootstrapFFT at the reference's active parameter set
 config 5: 128-bit fixed-point anticyclic FFT, N = 2048 / 4096, batch 16,384 (hp/code.cpp)
 """
 import importlib, json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 import oracle_lib as O

@@ -4,7 +4,7 @@ Needs the instrumented private build:  nvcc ... -DBR_TIMELINE -c csrc/br_kernels
 (see profiles/r1_notes.md).  The product library carries no instrumentation.
 """
 import ctypes, importlib, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 import oracle_lib as O
