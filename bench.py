@@ -302,7 +302,9 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             threads = host_threads()
             rate, kind, sample = cpu_gate_rate(threads * 256, threads)
-            line["cpu_baseline"] = {"value": rate, "unit": "gates/s", "cores": threads, "kind": kind, "sample": sample}
+            rate1, _, _ = cpu_gate_rate(64, 1)            # one thread, for comparison with the reference README's per-core figures
+            line["cpu_baseline"] = {"value": rate, "unit": "gates/s", "cores": threads, "kind": kind, "sample": sample,
+                                    "single_thread_value": rate1}
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
