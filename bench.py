@@ -294,6 +294,9 @@ def main():
                          "peak_source": "DFMA probe measured in this run (nominal 37.2 at 1965 MHz)",
                          "algorithmic": "94.72 MFLOP per gate bootstrap x gates per launch (SURVEY 8d)",
                          "l2_read_gbs_measured": l2_gbs},
+            "roofline_l2": {"bound": "l2", "achieved": 32.768e6 * B / (br_ms * 1e-3) / 1e9, "peak": l2_gbs, "unit": "GB/s",
+                            "note": "bootstrapping-key stream, 32.77 MB per bootstrap per accumulator (SURVEY 8d), against the L2 read "
+                                    "bandwidth measured in this run: the co-bound of the FP64 roofline, not the limiter"},
             "roofline_hbm": {"bound": "hbm", "achieved": HBM_BYTES_PER_GATE * B * args.steps / (ms_total * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "peak_source": hbm_src,
                              "note": "ciphertext I/O only (6012 B per gate); the 32.8 MB key stream is L2 resident"},
