@@ -82,13 +82,20 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // Ordering rule used throughout: a tcgen05.ld of columns this thread has stored needs tcgen05.wait::st in between.  The wait sits
 // in front of the LOADS (here, load_tmem, the stash reload), not behind the stores, so a store's latency overlaps with whatever
 // comes next (the following decomposition and transform) instead of being waited out on the spot.
-template <bool FIRST, typename BFn>
+// PIPE: the next chunk's load is in flight during this chunk's FMAs.  Pays for N = 2048 (+1.4 %), costs 4 % for N = 1024, where the
+// compiler overlaps the depth-8 butterflies with the plain loop (profiles/r1_notes.md) -- so it is a template choice.
+template <bool FIRST, bool PIPE = false, typename BFn>
 __device__ __forceinline__ void mac_tmem(const uint32_t taddr, const cplx (&v)[16], BFn b) {
     if (!FIRST) tmem_wait_st();
+    uint32_t rr[PIPE ? 2 : 1][16];
+    if (PIPE && !FIRST) TFHE_TLD16(rr[0], taddr);
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        uint32_t r[16];
-        if (!FIRST) { TFHE_TLD16(r, taddr + 16 * c); tmem_wait_ld(); }
+        uint32_t (&r)[16] = rr[PIPE ? (c & 1) : 0];
+        if (!FIRST) {
+            if (PIPE) { tmem_wait_ld(); if (c < 3) TFHE_TLD16(rr[PIPE ? ((c + 1) & 1) : 0], taddr + 16 * (c + 1)); }
+            else { TFHE_TLD16(r, taddr + 16 * c); tmem_wait_ld(); }
+        }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             cplx R = FIRST ? make_double2(0.0, 0.0)
@@ -215,9 +222,9 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
         TL(6);
         // (loading both accumulators' chunks together, or the next chunk during the FMAs, was 5 % slower each time: the compiler
         //  overlaps the depth-8 butterflies with this loop as it stands -- profiles/r1_notes.md)
-        mac_tmem<FIRST>(tacc, v, [&](int i) { return b0r[i]; });
+        mac_tmem<FIRST, LOGM == 10>(tacc, v, [&](int i) { return b0r[i]; });
         TL(7);
-        mac_tmem<FIRST>(tacc + 64, v, [&](int i) { return b1[i]; });
+        mac_tmem<FIRST, LOGM == 10>(tacc + 64, v, [&](int i) { return b1[i]; });
         TL(8);
     } else {
         tree_forward_c<LOGM, KM == KM_REGS2>(v, tw, t, ttw);
@@ -312,7 +319,7 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
         else        forward_and_mac<LOGM, false, KM>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp, tw, t, bar_id, ttw);
     }
     // every lane has finished reading the accumulator once it passes the first sync inside the backward transform
-    if constexpr (KM == KM_REGS2 && sizeof(Torus) == 4) {
+    if constexpr (KM == KM_REGS2) {
         // both polynomials together: no key values are in flight here, so there is room for two data sets (tree_fft.cuh)
         cplx R0[16], R1[16];
         TL(0);
