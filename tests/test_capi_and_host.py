@@ -105,3 +105,14 @@ def test_two_rank_gloo_sharding_and_key_broadcast(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/tfhe_b200.h must compile as C99 (no C++ or CUDA types in the signatures)."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "tfhe_b200.h"\nint main(void) { tfhe_b200_gate g = {0, 0, 0, 0, 0}; (void)g; return 0; }\n')
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
