@@ -296,9 +296,8 @@ __device__ __forceinline__ void tree_forward_c(cplx (&v)[16], const cplx* __rest
     constexpr int T = P::T;
     {   // depth 8
         if constexpr (TT) {
-            // (issued only now: the caller holds 128 registers of key values in flight across this stage)
+            Tw8Regs q; tw8_issue(q, ttw + 32);               // rides behind the lane exchange
             odd_swap(v, P::P >> 1);
-            Tw8Regs q; tw8_issue(q, ttw + 32);
             cplx E[8]; tw8_collect(E, q);
 #pragma unroll
             for (int m = 0; m < 8; m++) bf_fwd(v[2 * m], v[2 * m + 1], E[m]);
