@@ -70,6 +70,8 @@ _SIGS = {
     "tfhe_b200_bootsNOT_batch": [_P, _P, _P, _I, _P],
     "tfhe_b200_bootsMUX_batch": [_P, _P, _P, _P, _P, _I, _P],
     "tfhe_b200_circuit_eval_batch": [_P, _P, _I, _P, _I, _I, _P],
+    "tfhe_b200_gate_export_keys": [_P, _P, ctypes.POINTER(ctypes.c_size_t)],
+    "tfhe_b200_gate_import_keys": [_P, _P, ctypes.c_size_t],
     "tfhe_b200_tGswToFFTConvert_batch": [_P, _P, _P, _I, _I, _P],
     "tfhe_b200_tGswFFTExternMulToTLwe_batch": [_P, _P, _P, _I, _I, _I, _I, _P],
     "tfhe_b200_CMux_batch": [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P],
@@ -245,6 +247,20 @@ class Engine:
 
     def bootsMUX(self, result, a, b, c, count, stream=None):
         self._ck(self.lib.tfhe_b200_bootsMUX_batch(self.h, _ptr(result), _ptr(a), _ptr(b), _ptr(c), count, self._stream(stream)), "bootsMUX")
+
+    def export_gate_keys(self):
+        """the loaded gate keys in the engine's wire format (bytes-like numpy array)"""
+        import numpy as np
+        n = ctypes.c_size_t(0)
+        self._ck(self.lib.tfhe_b200_gate_export_keys(self.h, None, ctypes.byref(n)), "gate_export_keys")
+        buf = np.empty(n.value, np.uint8)
+        self._ck(self.lib.tfhe_b200_gate_export_keys(self.h, buf.ctypes.data, ctypes.byref(n)), "gate_export_keys")
+        return buf
+
+    def import_gate_keys(self, blob):
+        import numpy as np
+        b = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob)
+        self._ck(self.lib.tfhe_b200_gate_import_keys(self.h, b.ctypes.data, b.size), "gate_import_keys")
 
     def circuit_eval(self, gates, wires, n_wires, count, stream=None):
         """gates: int32 array [n_gates][5] = (op, out, in0, in1, in2) (tfhe_b200_gate); wires: device tensor [n_wires][count][n+1]."""

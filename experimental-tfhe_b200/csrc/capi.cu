@@ -212,6 +212,64 @@ int tfhe_b200_gate_key_blob(tfhe_b200_ctx* ctx, int which, void** dev_ptr, size_
     return TFHE_B200_OK;
 }
 
+/* ------------------------------------------------------------------ wire format of the loaded gate keys */
+struct KeyBlobHeader {            // 96 bytes, little endian
+    char magic[8];                // "TFHEB200"
+    uint32_t version, kind;       // kind 1 = gate keys
+    int32_t params[8];            // n, N, k, bk_l, bk_Bgbit, ks_t, ks_basebit, 0
+    uint64_t bk_bytes, ks_bytes, checksum;
+    uint64_t reserved[3];
+};
+static_assert(sizeof(KeyBlobHeader) == 96, "wire header is 96 bytes");
+static const uint32_t kKeyBlobVersion = 2;      // bump whenever the spectral slot order or the key-switch packing changes
+static uint64_t fnv1a(const unsigned char* p, size_t n, uint64_t h = 1469598103934665603ull) {
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+int tfhe_b200_gate_export_keys(tfhe_b200_ctx* ctx, void* buf_host, size_t* bytes) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    if (!ctx->gate_ready) return fail(ctx, TFHE_B200_ERR_NOKEY, "gate_export_keys: gate keys not loaded");
+    NEED(bytes, "gate_export_keys: null size pointer");
+    const size_t need = sizeof(KeyBlobHeader) + ctx->g_bkfft_bytes + ctx->g_ks_bytes;
+    if (!buf_host) { *bytes = need; return TFHE_B200_OK; }
+    NEED(*bytes >= need, "gate_export_keys: buffer too small");
+    CU(cudaSetDevice(ctx->device));
+    unsigned char* out = (unsigned char*)buf_host;
+    CU(cudaMemcpy(out + sizeof(KeyBlobHeader), ctx->g_bkfft, ctx->g_bkfft_bytes, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out + sizeof(KeyBlobHeader) + ctx->g_bkfft_bytes, ctx->g_ks, ctx->g_ks_bytes, cudaMemcpyDeviceToHost));
+    KeyBlobHeader h{};
+    memcpy(h.magic, "TFHEB200", 8);
+    h.version = kKeyBlobVersion; h.kind = 1;
+    const tfhe_b200_gate_params& p = ctx->gp;
+    const int32_t pv[8] = {p.n, p.N, p.k, p.bk_l, p.bk_Bgbit, p.ks_t, p.ks_basebit, 0};
+    memcpy(h.params, pv, sizeof(pv));
+    h.bk_bytes = ctx->g_bkfft_bytes; h.ks_bytes = ctx->g_ks_bytes;
+    h.checksum = fnv1a(out + sizeof(KeyBlobHeader), ctx->g_bkfft_bytes + ctx->g_ks_bytes);
+    memcpy(out, &h, sizeof(h));
+    *bytes = need;
+    return TFHE_B200_OK;
+}
+int tfhe_b200_gate_import_keys(tfhe_b200_ctx* ctx, const void* buf_host, size_t bytes) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(buf_host && bytes >= sizeof(KeyBlobHeader), "gate_import_keys: buffer too small for a header");
+    KeyBlobHeader h;
+    memcpy(&h, buf_host, sizeof(h));
+    NEED(memcmp(h.magic, "TFHEB200", 8) == 0, "gate_import_keys: bad magic");
+    NEED(h.version == kKeyBlobVersion, "gate_import_keys: key blob written by another format version");
+    NEED(h.kind == 1, "gate_import_keys: not a gate-key blob");
+    NEED(bytes == sizeof(KeyBlobHeader) + h.bk_bytes + h.ks_bytes, "gate_import_keys: size does not match the header");
+    const unsigned char* in = (const unsigned char*)buf_host + sizeof(KeyBlobHeader);
+    NEED(fnv1a(in, h.bk_bytes + h.ks_bytes) == h.checksum, "gate_import_keys: checksum mismatch");
+    tfhe_b200_gate_params p{h.params[0], h.params[1], h.params[2], h.params[3], h.params[4], h.params[5], h.params[6]};
+    int rc = tfhe_b200_gate_alloc_keys(ctx, &p); if (rc) return rc;
+    ctx->gate_ready = false;
+    NEED(ctx->g_bkfft_bytes == h.bk_bytes && ctx->g_ks_bytes == h.ks_bytes, "gate_import_keys: blob sizes do not match the parameters");
+    CU(cudaMemcpy(ctx->g_bkfft, in, h.bk_bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->g_ks, in + h.bk_bytes, h.ks_bytes, cudaMemcpyHostToDevice));
+    ctx->gate_ready = true;
+    return TFHE_B200_OK;
+}
+
 #define NEED_GATE() do { if (!ctx) return TFHE_B200_ERR_PARAM; if (!ctx->gate_ready) return fail(ctx, TFHE_B200_ERR_NOKEY, "gate keys not loaded"); } while (0)
 
 static BRArgs gate_br_args(const tfhe_b200_ctx* ctx, int count) {

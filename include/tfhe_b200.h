@@ -71,6 +71,13 @@ int tfhe_b200_gate_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p,
  * device blobs are broadcast (NCCL / cudaMemcpyPeer) by the caller.  which: 0 = bk spectra, 1 = ks. */
 int tfhe_b200_gate_alloc_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p);
 int tfhe_b200_gate_key_blob(tfhe_b200_ctx* ctx, int which, void** dev_ptr, size_t* bytes);
+/* Wire format of the LOADED gate keys (the reference has no serialization and rebuilds its keys on every run,
+ * cb/poc_CircuitBootstrapping.cpp:342-423): a 96-byte header -- magic "TFHEB200", format version, the seven parameters, the two
+ * blob sizes, an FNV-1a checksum of the payload -- followed by the bootstrapping-key spectra and the repacked key-switching key
+ * exactly as they sit in device memory, so importing is two copies and no transform.  The layout is private to a format version:
+ * import refuses other versions.  export: call with buf_host = NULL to get the size in *bytes, then with a buffer of that size. */
+int tfhe_b200_gate_export_keys(tfhe_b200_ctx* ctx, void* buf_host, size_t* bytes);
+int tfhe_b200_gate_import_keys(tfhe_b200_ctx* ctx, const void* buf_host, size_t bytes);
 
 /* tfhe_blindRotate_FFT (cb/lwe_functions.cpp:337-361): accum[B][2][N] in/out, bara[B][n] in [0,2N). */
 int tfhe_b200_blindRotate_FFT_batch(tfhe_b200_ctx* ctx, int32_t* accum_dev, const int32_t* bara_dev,

@@ -255,3 +255,35 @@ print("OK")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code, root], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_key_wire_format_roundtrip(gate_engine, gate_oracle):
+    """tfhe_b200_gate_export_keys / import_keys: a second context fed only the exported blob computes bit-identical gates; corrupted or
+    foreign blobs are refused (magic, version, size, checksum)."""
+    import importlib
+    mod = importlib.import_module("experimental-tfhe_b200")
+    g = gate_oracle
+    blob = gate_engine.export_gate_keys()
+    assert bytes(blob[:8]) == b"TFHEB200" and blob.size > 80_000_000
+    other = mod.Engine(0)
+    other.import_gate_keys(blob)
+    rng = np.random.default_rng(31)
+    B = 70
+    a = rng.integers(0, 2, size=B); b = rng.integers(0, 2, size=B)
+    ca, cb = dev(g.encrypt_bits(a, 61)), dev(g.encrypt_bits(b, 62))
+    o1 = torch.empty((B, g.n + 1), dtype=torch.int32, device=DEV); o2 = torch.empty_like(o1)
+    gate_engine.bootsGate("XOR", o1, ca, cb, B); other.bootsGate("XOR", o2, ca, cb, B)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2)
+    assert np.array_equal(g.decrypt_bits(o2.cpu().numpy()), a ^ b)
+    bad = blob.copy(); bad[200] ^= 1
+    with pytest.raises(mod.EngineError, match="checksum"):
+        other.import_gate_keys(bad)
+    bad = blob.copy(); bad[0] = ord("X")
+    with pytest.raises(mod.EngineError, match="magic"):
+        other.import_gate_keys(bad)
+    bad = blob.copy(); bad[8] ^= 0x40
+    with pytest.raises(mod.EngineError, match="version"):
+        other.import_gate_keys(bad)
+    with pytest.raises(mod.EngineError, match="size"):
+        other.import_gate_keys(blob[:-4])
