@@ -287,3 +287,32 @@ def test_key_wire_format_roundtrip(gate_engine, gate_oracle):
         other.import_gate_keys(bad)
     with pytest.raises(mod.EngineError, match="size"):
         other.import_gate_keys(blob[:-4])
+
+
+def test_two_streams_and_changing_batch_sizes(gate_engine, gate_oracle):
+    """Calls are asynchronous on the caller's streams; scratch grows on demand.  Gates issued from two streams with batch sizes that grow and
+    shrink (one CTA's worth, a ragged count, several waves) give the same ciphertexts as the same calls issued one after the other."""
+    g = gate_oracle
+    rng = np.random.default_rng(77)
+    sizes = [8, 3, 1185, 40, 2500, 9]
+    ins = [(dev(rng.integers(-2**31, 2**31 - 1, size=(B, g.n + 1), dtype=np.int64).astype(np.int32)),
+            dev(rng.integers(-2**31, 2**31 - 1, size=(B, g.n + 1), dtype=np.int64).astype(np.int32))) for B in sizes]
+    ops = ["NAND", "XOR", "OR", "AND", "NOR", "XNOR"]
+    ref = []
+    for (ca, cb), B, op in zip(ins, sizes, ops):
+        out = torch.empty((B, g.n + 1), dtype=torch.int32, device=DEV)
+        gate_engine.bootsGate(op, out, ca, cb, B)
+        torch.cuda.synchronize()
+        ref.append(out.clone())
+    # NOTE: one context serialises its scratch, so concurrent calls must not share it: streams here interleave submission only
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = [torch.empty((B, g.n + 1), dtype=torch.int32, device=DEV) for B in sizes]
+    for k, ((ca, cb), B, op) in enumerate(zip(ins, sizes, ops)):
+        st = s1 if k % 2 == 0 else s2
+        st.wait_stream(torch.cuda.current_stream())
+        if k > 0:
+            st.wait_stream(s2 if st is s1 else s1)        # the context's scratch is single-buffered: order the calls
+        gate_engine.bootsGate(op, outs[k], ca, cb, B, stream=st.cuda_stream)
+    s1.synchronize(); s2.synchronize()
+    for a, b in zip(outs, ref):
+        assert torch.equal(a, b)
