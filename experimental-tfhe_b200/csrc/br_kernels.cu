@@ -165,7 +165,7 @@ __device__ __forceinline__ void load_tmem(cplx (&R)[16], const uint32_t taddr) {
 //             consumes it, chunk by chunk, the freed registers take BK[p][1] (12 warps per SM at 168 registers)
 //   KM_TMEM : they wait in tensor memory (KeyPipe, bk_pipe.cuh), no key registers at all (12 warps per SM)
 enum { KM_REGS2 = 0, KM_TMEM = 1, KM_REGS1 = 2 };
-template <int LOGM, bool FIRST, int KM>
+template <int LOGM, bool FIRST, int KM, bool NOTT9 = false>
 __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t tacc, const cplx* __restrict__ bkp,
                                                 cplx* __restrict__ buf, KeyPipe& kp,
                                                 const cplx* __restrict__ tw, const int t, const int bar_id, const uint32_t ttw) {
@@ -186,7 +186,7 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
         cplx kb[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) kb[i] = __ldg(g0 + i * P::T);
-        tree_forward_c<LOGM, KM == KM_REGS2>(v, tw, t, ttw);
+        tree_forward_c<LOGM, KM == KM_REGS2, KM == KM_REGS2 && !(NOTT9)>(v, tw, t, ttw);
         TL(6);
         // R0 += v * BK[p][0]; each consumed chunk's registers are refilled with the same slots of BK[p][1]
 #pragma unroll
@@ -218,7 +218,7 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
 #pragma unroll
         for (int i = 0; i < 16; i++) b0r[i] = __ldg(g1 - P::M + i * P::T);
         TL(5);
-        tree_forward_c<LOGM, KM == KM_REGS2>(v, tw, t, ttw);
+        tree_forward_c<LOGM, KM == KM_REGS2, KM == KM_REGS2 && !(NOTT9)>(v, tw, t, ttw);
         TL(6);
         // (loading both accumulators' chunks together, or the next chunk during the FMAs, was 5 % slower each time: the compiler
         //  overlaps the depth-8 butterflies with this loop as it stands -- profiles/r1_notes.md)
@@ -227,7 +227,7 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
         mac_tmem<FIRST, LOGM == 10>(tacc + 64, v, [&](int i) { return b1[i]; });
         TL(8);
     } else {
-        tree_forward_c<LOGM, KM == KM_REGS2>(v, tw, t, ttw);
+        tree_forward_c<LOGM, KM == KM_REGS2, KM == KM_REGS2 && !(NOTT9)>(v, tw, t, ttw);
         TL(6);
         kp.acquire(t & 31);
         TL(16);
@@ -315,8 +315,8 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
             // (no wait::st here: the reload at the next level waits)
         }
         TL(1);
-        if (p == 0) forward_and_mac<LOGM, true, KM>(v, tacc, bk, buf, kp, tw, t, bar_id, ttw);
-        else        forward_and_mac<LOGM, false, KM>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp, tw, t, bar_id, ttw);
+        if (p == 0) forward_and_mac<LOGM, true, KM, STASH && sizeof(Torus) == 8>(v, tacc, bk, buf, kp, tw, t, bar_id, ttw);
+        else        forward_and_mac<LOGM, false, KM, STASH && sizeof(Torus) == 8>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp, tw, t, bar_id, ttw);
     }
     // every lane has finished reading the accumulator once it passes the first sync inside the backward transform
     if constexpr (KM == KM_REGS2) {
@@ -325,7 +325,7 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
         TL(0);
         load_tmem2(R0, R1, tacc);
         TL(9);
-        tree_backward2<LOGM, true>(R0, R1, buf, tw, t, bar_id, ttw);
+        tree_backward2<LOGM, true, !(STASH && sizeof(Torus) == 8)>(R0, R1, buf, tw, t, bar_id, ttw);
 #pragma unroll
         for (int m = 0; m < 16; m++) {
             const int j = t + T * m;
@@ -386,7 +386,9 @@ template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM> struct BRSme
     static_assert(TOTAL <= 232448, "shared memory budget (227 KB) exceeded");
     static constexpr bool TWT = KM == KM_REGS2;                                         // per-lane twiddles in tensor memory (tree_fft.cuh)
     static constexpr int TW_COL = 128 + (STASH ? 4 * StashWords<Torus>::PER_C : 0);
-    static constexpr int TMEM_COLS = TW_COL + (TWT ? 32 * (2 + (P::NS > 1 ? 1 : 0)) : 0);
+    // depth-9 twiddles (N = 2048) stay in shared memory when the 64-column stash of Torus64 needs their place
+    static constexpr bool TT9 = TWT && P::NS > 1 && !(STASH && sizeof(Torus) == 8);
+    static constexpr int TMEM_COLS = TW_COL + (TWT ? 32 * (2 + (TT9 ? 1 : 0)) : 0);
     static constexpr int KEY_COL = (WARPS + 3) / 4 * TMEM_COLS;
     static_assert(KEY_COL + (KM == KM_TMEM ? 128 : 0) <= 512, "tensor memory columns exceeded");
     static_assert(KM != KM_TMEM || P::T == 32, "KeyPipe: one warp per accumulator");
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
     const uint32_t tmem_base = *tmem_base_slot;
     const uint32_t tacc = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)S::TMEM_COLS;   // R0 | R1 | stash
     const uint32_t ttw = S::TWT ? tacc + (uint32_t)S::TW_COL : 0u;
-    if (S::TWT) tree_twiddles_to_tmem<LOGM>(tw, t, ttw);
+    if (S::TWT) tree_twiddles_to_tmem<LOGM, S::TT9 || LOGM == 9>(tw, t, ttw);
     KeyPipe kp{kps, smem_raw + S::TW_BYTES + S::CTRL_BYTES, reinterpret_cast<const unsigned char*>(A.bkfft),
                tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)S::KEY_COL, tmem_base + (uint32_t)S::KEY_COL,
                (uint32_t)S::CHUNK_BYTES, (uint32_t)(A.n * 2 * A.l), 0u};
@@ -612,6 +614,7 @@ cudaError_t blind_rotate_init() {
     if ((e = br_attr<9, int32_t, G32, true, KM_REGS2>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32, false, KM_REGS2>()) != cudaSuccess) return e;
     if ((e = br_attr<10, int64_t, G64, false, KM_REGS2>()) != cudaSuccess) return e;
+    if ((e = br_attr<10, int64_t, G64, true, KM_REGS2>()) != cudaSuccess) return e;
     g_inited = true;
     return cudaSuccess;
 }
@@ -630,9 +633,11 @@ cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
     if (!g_inited) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
     if (a.count <= 0) return cudaSuccess;
     const long units = (long)a.count * (a.n_mu > 0 ? a.n_mu : 1);
-    // no stash for Torus64: 64 columns of u per lane cost more tensor-memory traffic than the re-reads save (232 vs 225 ms
-    // per 4096 circuit bootstraps, profiles/r1_notes.md)
-    return br_launch<10, int64_t, G64, false, KM_REGS2>(a, units, s);
+    // Torus64: the stash takes 64 columns, so the depth-9 twiddles stay in shared memory (R 128 | stash 64 | twiddles 64 = 256 columns).
+    // With the waits deferred the stash pays here too (189 vs 201 ms per 4096 circuit bootstraps; before that it cost 3 %).
+    static const char* variant = getenv("TFHE_B200_BR_VARIANT");
+    if (variant && variant[0] == 'n') return br_launch<10, int64_t, G64, false, KM_REGS2>(a, units, s);      // "nostash"
+    return br_launch<10, int64_t, G64, true, KM_REGS2>(a, units, s);
 }
 
 // ---------------------------------------------------------------------------------------------

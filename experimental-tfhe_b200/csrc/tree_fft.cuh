@@ -262,7 +262,7 @@ __device__ __forceinline__ void tree_forward_a(cplx (&v)[16], cplx* __restrict__
     TL(3);
 }
 // this lane's post-transpose twiddles -> its tensor-memory columns at ttw (once per kernel)
-template <int LOGM>
+template <int LOGM, bool TT9 = true>
 __device__ __forceinline__ void tree_twiddles_to_tmem(const cplx* __restrict__ tw, const int t, const uint32_t ttw) {
     typedef TreePlan<LOGM> P;
     cplx E[8];
@@ -272,7 +272,7 @@ __device__ __forceinline__ void tree_twiddles_to_tmem(const cplx* __restrict__ t
 #pragma unroll
     for (int m = 0; m < 8; m++) E[m] = tw[P::TC0 + m * P::T + t];
     tw8_to_tmem(E, ttw + 32);
-    if (P::NS > 1) {
+    if (P::NS > 1 && TT9) {
 #pragma unroll
         for (int m = 0; m < 8; m++) E[m] = tw[P::TC1 + m * P::T + t];
         tw8_to_tmem(E, ttw + 64);
@@ -290,7 +290,7 @@ __device__ __forceinline__ void tree_forward_b_tm(cplx (&v)[16], const Tw8Regs& 
     tw8_collect(E, q);
     pass16<false>(v, E, 1);
 }
-template <int LOGM, bool TT = false>
+template <int LOGM, bool TT = false, bool TT9 = TT>
 __device__ __forceinline__ void tree_forward_c(cplx (&v)[16], const cplx* __restrict__ tw, const int t, const uint32_t ttw = 0) {      // depths 8..
     typedef TreePlan<LOGM> P;
     constexpr int T = P::T;
@@ -309,7 +309,7 @@ __device__ __forceinline__ void tree_forward_c(cplx (&v)[16], const cplx* __rest
         }
     }
     if (P::NS > 1) {   // depth 9 (M = 1024)
-        if constexpr (TT) {
+        if constexpr (TT9) {
             odd_swap(v, 1);
             Tw8Regs q; tw8_issue(q, ttw + 64);
             cplx E[8]; tw8_collect(E, q);
@@ -383,7 +383,7 @@ __device__ __forceinline__ void tree_backward(cplx (&v)[16], cplx* __restrict__ 
 // Two backward transforms side by side (the two polynomials of a TLWE accumulator): the stages are interleaved so each
 // latency-bound step (twiddle fetch, lane exchange, transpose) is paid once for two independent data sets, and the twiddles are
 // fetched once.  Uses the one transpose buffer twice.  Needs 128 data registers: only where no key values are in flight.
-template <int LOGM, bool TT = false>
+template <int LOGM, bool TT = false, bool TT9 = TT>
 __device__ __forceinline__ void tree_backward2(cplx (&v)[16], cplx (&u)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t,
                                                const int bar_id, const uint32_t ttw = 0) {
     typedef TreePlan<LOGM> P;
@@ -392,8 +392,9 @@ __device__ __forceinline__ void tree_backward2(cplx (&v)[16], cplx (&u)[16], cpl
     Tw8Regs qn;
     if (P::NS > 1) {
         cplx E[8];
-        if constexpr (TT) { Tw8Regs q; tw8_issue(q, ttw + 64); tw8_issue(qn, ttw + 32); tw8_collect(E, q); }
+        if constexpr (TT9) { Tw8Regs q; tw8_issue(q, ttw + 64); tw8_issue(qn, ttw + 32); tw8_collect(E, q); }
         else {
+            if constexpr (TT) tw8_issue(qn, ttw + 32);
 #pragma unroll
             for (int m = 0; m < 8; m++) E[m] = tw[P::TC1 + m * T + t];
         }
