@@ -90,3 +90,42 @@ def test_circuit_eval_errors(gate_engine, gate_oracle):
     with pytest.raises(mod.EngineError):
         gate_engine.circuit_eval(np.array([(12, 1, 0, 1, 0)], np.int32), wires, 2, 4)            # unknown op
     gate_engine.circuit_eval(np.zeros((0, 5), np.int32), wires, 2, 4)                             # empty netlist is fine
+
+
+def test_circuit_in_a_cuda_graph(gate_engine, gate_oracle):
+    """After a warm-up call nothing is allocated or synchronised inside tfhe_b200_circuit_eval_batch, so a whole circuit can be captured
+    into a CUDA graph and replayed ("each circuit level is one batched gate launch (CUDA graph)")."""
+    g = gate_oracle
+    bits, B = 4, 24
+    rng = np.random.default_rng(3)
+    A = rng.integers(0, 2**bits, size=B, dtype=np.uint64); Bv = rng.integers(0, 2**bits, size=B, dtype=np.uint64)
+    gates, w = adder_netlist(bits)
+    wires = torch.zeros((w["n_wires"], B, g.n + 1), dtype=torch.int32, device=DEV)
+
+    def load_inputs(Av, Bw, seed):
+        for i in range(bits):
+            wires[w["a0"] + i] = torch.from_numpy(g.encrypt_bits((Av >> np.uint64(i)) & np.uint64(1), seed + i)).to(DEV)
+            wires[w["b0"] + i] = torch.from_numpy(g.encrypt_bits((Bw >> np.uint64(i)) & np.uint64(1), seed + 100 + i)).to(DEV)
+        wires[w["cin"]] = torch.from_numpy(g.encrypt_bits(np.zeros(B, np.int64), seed + 200)).to(DEV)
+
+    def read_sum():
+        res = wires.cpu().numpy()
+        total = np.zeros(B, np.uint64)
+        for i in range(bits):
+            total |= g.decrypt_bits(res[w["s0"] + i]).astype(np.uint64) << np.uint64(i)
+        return total | (g.decrypt_bits(res[w["c0"] + bits]).astype(np.uint64) << np.uint64(bits))
+
+    load_inputs(A, Bv, 500)
+    gate_engine.circuit_eval(gates, wires, w["n_wires"], B)           # warm-up: sizes the scratch
+    torch.cuda.synchronize()
+    assert np.array_equal(read_sum(), A + Bv)
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.graph(graph, stream=s):
+        gate_engine.circuit_eval(gates, wires, w["n_wires"], B, stream=torch.cuda.current_stream().cuda_stream)
+    A2 = rng.integers(0, 2**bits, size=B, dtype=np.uint64); B2 = rng.integers(0, 2**bits, size=B, dtype=np.uint64)
+    load_inputs(A2, B2, 900)                                          # new inputs in the captured buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(read_sum(), A2 + B2)
