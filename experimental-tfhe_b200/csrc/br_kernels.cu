@@ -570,11 +570,11 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) extern_mul_kern
 cudaError_t launch_extern_mul32(const BRArgs& a, cudaStream_t s) {
     constexpr int G = 8;
     typedef BRSmem<9, int32_t, G, true, KM_REGS2> S;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.need()) {
         cudaError_t e = cudaFuncSetAttribute(extern_mul_kernel<9, int32_t, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.done();
     }
     if (a.count <= 0) return cudaSuccess;
     extern_mul_kernel<9, int32_t, G><<<(a.count + G - 1) / G, G * TreePlan<9>::T, S::TOTAL, s>>>(a);
@@ -588,7 +588,7 @@ extern "C" __attribute__((visibility("default"))) int tfhe_b200_dev_timeline(lon
 }
 namespace tfhe_b200 {
 #endif
-static bool g_inited = false;
+static PerDeviceOnce g_inited;
 // Configurations (profiles/r1_notes.md has the sweep):
 //   default:  8 warps per SM, key prefetched into registers, stash                    <9, int32,  8, true,  KM_REGS2> 174 k/s
 //   half   : 12 warps per SM, one key polynomial's worth of registers (KM_REGS1), stash <9, int32, 12, true,  KM_REGS1> 164 k/s
@@ -615,12 +615,12 @@ cudaError_t blind_rotate_init() {
     if ((e = br_attr<9, int32_t, G32, false, KM_REGS2>()) != cudaSuccess) return e;
     if ((e = br_attr<10, int64_t, G64, false, KM_REGS2>()) != cudaSuccess) return e;
     if ((e = br_attr<10, int64_t, G64, true, KM_REGS2>()) != cudaSuccess) return e;
-    g_inited = true;
+    g_inited.done();
     return cudaSuccess;
 }
 
 cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
-    if (!g_inited) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
+    if (g_inited.need()) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
     if (a.count <= 0) return cudaSuccess;
     // development knob: TFHE_B200_BR_VARIANT = keytm | half | nostash selects the measured alternatives
     static const char* variant = getenv("TFHE_B200_BR_VARIANT");
@@ -630,7 +630,7 @@ cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
     return br_launch<9, int32_t, G32, true, KM_REGS2>(a, a.count, s);
 }
 cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
-    if (!g_inited) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
+    if (g_inited.need()) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
     if (a.count <= 0) return cudaSuccess;
     const long units = (long)a.count * (a.n_mu > 0 ? a.n_mu : 1);
     // Torus64: the stash takes 64 columns, so the depth-9 twiddles stay in shared memory (R 128 | stash 64 | twiddles 64 = 256 columns).

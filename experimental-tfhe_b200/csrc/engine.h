@@ -9,6 +9,14 @@ namespace tfhe_b200 {
 
 typedef double2 cplx;
 
+// cudaFuncSetAttribute is per DEVICE: "done" flags for the opt-in shared-memory sizes are kept per device ordinal, so a process
+// that opens contexts on several GPUs configures each of them.
+struct PerDeviceOnce {
+    unsigned long long mask = 0;
+    bool need() const { int d = 0; cudaGetDevice(&d); return !((mask >> (d & 63)) & 1ull); }
+    void done() { int d = 0; cudaGetDevice(&d); mask |= 1ull << (d & 63); }
+};
+
 // host-side twiddle generation (twiddles.cpp): TreePlan<LOGM> layout (tree_fft.cuh), entries are (re,im) pairs
 void make_fft_tables(int logM, double* out /* 2 * TW_TOTAL doubles */);
 int  fft_table_entries(int logM);

@@ -194,13 +194,13 @@ template <typename TorusIn, int BASEBIT>
 static cudaError_t launch_ks_b(const KSArgs& a, cudaStream_t s) {
     typedef typename std::conditional<sizeof(TorusIn) == 4, uint32_t, uint64_t>::type U;
     constexpr size_t smem = ks_smem_bytes<U, BASEBIT>();
-    static bool attr_done = false;               // per instantiation
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;              // per instantiation and device
+    if (attr_done.need()) {
         cudaError_t e = cudaFuncSetAttribute(keyswitch_kernel<TorusIn, BASEBIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(keyswitch_kernel<TorusIn, BASEBIT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.done();
     }
     dim3 grid((a.count + KS_TILE - 1) / KS_TILE, a.cols_pad / 512, a.nz > 0 ? a.nz : 1);
     keyswitch_kernel<TorusIn, BASEBIT><<<grid, KS_THREADS, smem, s>>>(a);

@@ -316,3 +316,24 @@ def test_two_streams_and_changing_batch_sizes(gate_engine, gate_oracle):
     s1.synchronize(); s2.synchronize()
     for a, b in zip(outs, ref):
         assert torch.equal(a, b)
+
+
+def test_one_process_two_devices(gate_oracle):
+    """Kernel attributes (opt-in shared memory) are per device: a process that opens contexts on two GPUs gets working kernels on both."""
+    import importlib
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    mod = importlib.import_module("experimental-tfhe_b200")
+    g = gate_oracle
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 2, 40); b = rng.integers(0, 2, 40)
+    ca, cb = g.encrypt_bits(a, 1), g.encrypt_bits(b, 2)
+    for d in (1, 0):
+        torch.cuda.set_device(d)
+        eng = mod.Engine(d)
+        eng.load_gate_keys(g.engine_params(), g.bk, g.ks)
+        out = torch.empty((40, g.n + 1), dtype=torch.int32, device=f"cuda:{d}")
+        eng.bootsGate("NAND", out, torch.from_numpy(ca).to(f"cuda:{d}"), torch.from_numpy(cb).to(f"cuda:{d}"), 40)
+        torch.cuda.synchronize(d)
+        assert np.array_equal(g.decrypt_bits(out.cpu().numpy()), 1 - (a & b)), d
+    torch.cuda.set_device(0)
