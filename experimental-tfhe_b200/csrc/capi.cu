@@ -35,6 +35,8 @@ struct tfhe_b200_ctx {
     // scratch (grown on demand, never per call once warm)
     void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[4] = {0, 0, 0, 0};
+    // two private streams for the chunked host-buffer path (copies of one chunk overlap the kernels of another)
+    cudaStream_t hs[2] = {nullptr, nullptr};
     // profiling (diagnostics): events around every launch when enabled
     bool profiling = false;
     struct Span { cudaEvent_t a, b; int cat; };
@@ -124,6 +126,7 @@ int tfhe_b200_ctx_create(tfhe_b200_ctx** out, int device) {
 int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx) {
     if (!ctx) return TFHE_B200_OK;
     cudaSetDevice(ctx->device);
+    for (int k = 0; k < 2; k++) if (ctx->hs[k]) cudaStreamDestroy(ctx->hs[k]);
     cudaFree(ctx->tw1024); cudaFree(ctx->tw2048);
     cudaFree(ctx->g_bkfft); cudaFree(ctx->g_ks);
     cudaFree(ctx->c_bkfft); cudaFree(ctx->c_preks); cudaFree(ctx->c_privks);
@@ -367,16 +370,35 @@ int tfhe_b200_bootsMUX_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int3
 int tfhe_b200_bootsGate_batch_host(tfhe_b200_ctx* ctx, int op, int32_t* result_host, const int32_t* ca_host, const int32_t* cb_host, int count) {
     NEED_GATE(); NEED(op >= 0 && op < TFHE_B200_NUM_GATES, "bootsGate: unknown gate");
     NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_host && ca_host && cb_host), "null buffer");
+    if (count == 0) return TFHE_B200_OK;
     CU(cudaSetDevice(ctx->device));
-    const size_t bytes = (size_t)count * (ctx->gp.n + 1) * sizeof(int32_t);
+    const size_t row = (size_t)ctx->gp.n + 1, urow = (size_t)ctx->gp.N + 1;
+    const size_t bytes = (size_t)count * row * sizeof(int32_t);
     int rc = ensure_scratch(ctx, 2, 2 * bytes); if (rc) return rc;
     rc = ensure_scratch(ctx, 3, bytes); if (rc) return rc;
-    int32_t* da = (int32_t*)ctx->scratch[2]; int32_t* db = da + (size_t)count * (ctx->gp.n + 1); int32_t* dr = (int32_t*)ctx->scratch[3];
-    CU(cudaMemcpyAsync(da, ca_host, bytes, cudaMemcpyHostToDevice, 0));
-    CU(cudaMemcpyAsync(db, cb_host, bytes, cudaMemcpyHostToDevice, 0));
-    rc = tfhe_b200_bootsGate_batch(ctx, op, dr, da, db, count, nullptr); if (rc) return rc;
-    CU(cudaMemcpyAsync(result_host, dr, bytes, cudaMemcpyDeviceToHost, 0));
-    CU(cudaStreamSynchronize(0));
+    rc = ensure_scratch(ctx, 0, (size_t)count * urow * sizeof(int32_t)); if (rc) return rc;
+    int32_t* da = (int32_t*)ctx->scratch[2]; int32_t* db = da + (size_t)count * row; int32_t* dr = (int32_t*)ctx->scratch[3];
+    int32_t* u = (int32_t*)ctx->scratch[0];
+    for (int k = 0; k < 2; k++) if (!ctx->hs[k]) CU(cudaStreamCreateWithFlags(&ctx->hs[k], cudaStreamNonBlocking));
+    // Chunks of whole waves (8 accumulators per SM), alternating between two streams: the host->device copies of chunk k+1 and the
+    // device->host copy of chunk k-1 run under the kernels of chunk k, and the blind rotations of consecutive chunks fill each other's
+    // last wave.  Small batches go through as one chunk.
+    const int wave = 8 * ctx->sm_count;
+    const int nchunk = count >= 8 * wave ? 4 : (count >= 2 * wave ? 2 : 1);
+    const int per = ((count + nchunk - 1) / nchunk + wave - 1) / wave * wave;
+    const int32_t cst = (int32_t)((uint32_t)kGate[op].c8 * (uint32_t)kMU);
+    for (int k = 0, off = 0; off < count; k++, off += per) {
+        const int c = count - off < per ? count - off : per;
+        cudaStream_t s = ctx->hs[k & 1];
+        const size_t o = (size_t)off * row, cb = (size_t)c * row * sizeof(int32_t);
+        CU(cudaMemcpyAsync(da + o, ca_host + o, cb, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(db + o, cb_host + o, cb, cudaMemcpyHostToDevice, s));
+        rc = bootstrap_woks(ctx, u + (size_t)off * urow, kMU, da + o, db + o, kGate[op].ka, kGate[op].kb, cst, c, s); if (rc) return rc;
+        rc = gate_keyswitch(ctx, dr + o, u + (size_t)off * urow, c, s); if (rc) return rc;
+        CU(cudaMemcpyAsync(result_host + o, dr + o, cb, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(ctx->hs[0]));
+    CU(cudaStreamSynchronize(ctx->hs[1]));
     return TFHE_B200_OK;
 }
 

@@ -111,7 +111,8 @@ int tfhe_b200_bootsNOT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int3
 int tfhe_b200_bootsMUX_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* a_dev, const int32_t* b_dev,
                              const int32_t* c_dev, int count, void* stream);
 /* Same gate call on HOST buffers: H2D of ca/cb, the gate, D2H of result, all inside the call
- * (this is the end-to-end path a reference user would bind). */
+ * (this is the end-to-end path a reference user would bind).  Large batches are cut into chunks of whole waves on two private
+ * streams so that the copies of one chunk run under the kernels of another; pinned host buffers make the copies asynchronous. */
 int tfhe_b200_bootsGate_batch_host(tfhe_b200_ctx* ctx, int op, int32_t* result_host, const int32_t* ca_host,
                                    const int32_t* cb_host, int count);
 

@@ -337,3 +337,20 @@ def test_one_process_two_devices(gate_oracle):
         torch.cuda.synchronize(d)
         assert np.array_equal(g.decrypt_bits(out.cpu().numpy()), 1 - (a & b)), d
     torch.cuda.set_device(0)
+
+
+def test_host_api_chunked_matches_device_api(gate_engine, gate_oracle):
+    """tfhe_b200_bootsGate_batch_host splits large batches into whole-wave chunks on two streams (copies overlap kernels); the
+    result must be the device API's, bit for bit, at sizes that give 1, 2 and 4 chunks with a ragged tail."""
+    g = gate_oracle
+    wave = 8 * gate_engine.sm_count()
+    rng = np.random.default_rng(123)
+    for B in (wave - 5, 2 * wave + 37, 8 * wave + 11):
+        ca = rng.integers(-2**31, 2**31 - 1, size=(B, g.n + 1), dtype=np.int64).astype(np.int32)
+        cb = rng.integers(-2**31, 2**31 - 1, size=(B, g.n + 1), dtype=np.int64).astype(np.int32)
+        out_dev = torch.empty((B, g.n + 1), dtype=torch.int32, device=DEV)
+        gate_engine.bootsGate("ORYN", out_dev, dev(ca), dev(cb), B)
+        torch.cuda.synchronize()
+        out_host = np.zeros((B, g.n + 1), np.int32)
+        gate_engine.bootsGate_host("ORYN", out_host, ca, cb, B)
+        assert np.array_equal(out_host, out_dev.cpu().numpy()), B
