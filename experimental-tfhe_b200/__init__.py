@@ -61,6 +61,14 @@ _SIGS = {
     "tfhe_b200_gate_load_keys": [_P, ctypes.POINTER(GateParams), _P, _P],
     "tfhe_b200_gate_alloc_keys": [_P, ctypes.POINTER(GateParams)],
     "tfhe_b200_gate_key_blob": [_P, _I, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_size_t)],
+    "tfhe_b200_gate_commit_keys": [_P],
+    "tfhe_b200_cb_alloc_keys": [_P, ctypes.POINTER(CBParams), _I],
+    "tfhe_b200_cb_key_blob": [_P, _I, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_size_t)],
+    "tfhe_b200_cb_commit_keys": [_P],
+    "tfhe_b200_cb_export_keys": [_P, _P, ctypes.POINTER(ctypes.c_size_t)],
+    "tfhe_b200_cb_import_keys": [_P, _P, ctypes.c_size_t],
+    "tfhe_b200_ciphertext_pack": [_I, _P, _P, _P, ctypes.POINTER(ctypes.c_size_t)],
+    "tfhe_b200_ciphertext_unpack": [_P, ctypes.c_size_t, ctypes.POINTER(_I), _P, _P, ctypes.POINTER(ctypes.c_size_t)],
     "tfhe_b200_blindRotate_FFT_batch": [_P, _P, _P, _I, _P],
     "tfhe_b200_blindRotateAndExtract_FFT_batch": [_P, _P, _P, _P, _P, _I, _P],
     "tfhe_b200_bootstrap_woKS_FFT_batch": [_P, _P, ctypes.c_int32, _P, _I, _P],
@@ -126,6 +134,43 @@ def _ptr(x):
     if hasattr(x, "ctypes"):
         return x.ctypes.data
     return int(x)
+
+
+CT_KINDS = {"LWE32": 1, "LWE64": 2, "TLWE32": 3, "TGSW32": 4}
+
+
+def ciphertext_pack(kind, samples):
+    """numpy array of samples -> wire blob (tfhe_b200_ciphertext_pack); kind in CT_KINDS"""
+    import numpy as np
+    lib = load()
+    a = np.ascontiguousarray(samples)
+    dims = (ctypes.c_int64 * 4)(*(list(a.shape) + [0] * (4 - a.ndim)))
+    n = ctypes.c_size_t()
+    rc = lib.tfhe_b200_ciphertext_pack(CT_KINDS[kind], dims, None, None, ctypes.byref(n))
+    if rc != OK:
+        raise EngineError(f"ciphertext_pack failed ({rc}): {lib.tfhe_b200_last_error(None).decode()}")
+    buf = np.empty(n.value, np.uint8)
+    rc = lib.tfhe_b200_ciphertext_pack(CT_KINDS[kind], dims, _ptr(a), _ptr(buf), ctypes.byref(n))
+    if rc != OK:
+        raise EngineError(f"ciphertext_pack failed ({rc}): {lib.tfhe_b200_last_error(None).decode()}")
+    return buf
+
+
+def ciphertext_unpack(blob):
+    """wire blob -> (kind name, numpy array)"""
+    import numpy as np
+    lib = load()
+    kind = _I(); dims = (ctypes.c_int64 * 4)(); n = ctypes.c_size_t()
+    rc = lib.tfhe_b200_ciphertext_unpack(_ptr(blob), int(blob.nbytes), ctypes.byref(kind), dims, None, ctypes.byref(n))
+    if rc != OK:
+        raise EngineError(f"ciphertext_unpack failed ({rc}): {lib.tfhe_b200_last_error(None).decode()}")
+    name = [k for k, v in CT_KINDS.items() if v == kind.value][0]
+    shape = [d for d in dims if d > 0]
+    out = np.empty(shape, np.int64 if name == "LWE64" else np.int32)
+    rc = lib.tfhe_b200_ciphertext_unpack(_ptr(blob), int(blob.nbytes), None, None, _ptr(out), ctypes.byref(n))
+    if rc != OK:
+        raise EngineError(f"ciphertext_unpack failed ({rc}): {lib.tfhe_b200_last_error(None).decode()}")
+    return name, out
 
 
 class Engine:
@@ -204,6 +249,9 @@ class Engine:
         p = GateParams(**params) if isinstance(params, dict) else params
         self._ck(self.lib.tfhe_b200_gate_alloc_keys(self.h, ctypes.byref(p)), "gate_alloc_keys")
         self.gate_params = p
+
+    def commit_gate_keys(self):
+        self._ck(self.lib.tfhe_b200_gate_commit_keys(self.h), "gate_commit_keys")
 
     def gate_key_blob(self, which):
         ptr, nbytes = _P(), ctypes.c_size_t()
@@ -310,6 +358,31 @@ class Engine:
         p = CBParams(**params) if isinstance(params, dict) else params
         self._ck(self.lib.tfhe_b200_cb_load_keys(self.h, ctypes.byref(p), _ptr(preKS_host), _ptr(bk_host), _ptr(privKS_host)), "cb_load_keys")
         self.cb_params = p
+
+    def alloc_cb_keys(self, params, with_privks=True):
+        p = CBParams(**params) if isinstance(params, dict) else params
+        self._ck(self.lib.tfhe_b200_cb_alloc_keys(self.h, ctypes.byref(p), int(with_privks)), "cb_alloc_keys")
+        self.cb_params = p
+
+    def cb_key_blob(self, which):
+        ptr, nbytes = _P(), ctypes.c_size_t()
+        self._ck(self.lib.tfhe_b200_cb_key_blob(self.h, which, ctypes.byref(ptr), ctypes.byref(nbytes)), "cb_key_blob")
+        return ptr.value, nbytes.value
+
+    def commit_cb_keys(self):
+        self._ck(self.lib.tfhe_b200_cb_commit_keys(self.h), "cb_commit_keys")
+
+    def export_cb_keys(self):
+        """numpy uint8 blob: header + the three device key blobs (tfhe_b200_cb_export_keys)"""
+        import numpy as np
+        n = ctypes.c_size_t()
+        self._ck(self.lib.tfhe_b200_cb_export_keys(self.h, None, ctypes.byref(n)), "cb_export_keys(size)")
+        buf = np.empty(n.value, np.uint8)
+        self._ck(self.lib.tfhe_b200_cb_export_keys(self.h, _ptr(buf), ctypes.byref(n)), "cb_export_keys")
+        return buf
+
+    def import_cb_keys(self, blob):
+        self._ck(self.lib.tfhe_b200_cb_import_keys(self.h, _ptr(blob), int(blob.nbytes)), "cb_import_keys")
 
     def preKeySwitch(self, result, x, count, stream=None):
         self._ck(self.lib.tfhe_b200_preKeySwitch_batch(self.h, _ptr(result), _ptr(x), count, self._stream(stream)), "preKeySwitch")

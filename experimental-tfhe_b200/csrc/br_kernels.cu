@@ -240,11 +240,195 @@ __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t ta
     }
 }
 
+template <typename Torus> struct StashWords { static constexpr int PER_C = 8 * (int)(sizeof(Torus) / 4); };   // words per c (4 complex)
+// ---------------------------------------------------------------------------------------------
+// Two digit polynomials at once (gadget levels lev, lev+1 of one accumulator polynomial): forward transforms side by side
+// (tree_forward2) and ONE pass over the spectral accumulators for both,
+//     R0 += v (.) BK[p][0] + u (.) BK[p+1][0],   R1 += v (.) BK[p][1] + u (.) BK[p+1][1]
+// so each tensor-memory round trip carries 16 FMAs per slot instead of 8 and happens half as often.  The four key values of a
+// slot ride in a rolling register window KW slots deep: the first KW slots are requested before depths 4-7 (their L2 round trip
+// hides behind two transforms' worth of butterflies), and every slot that has been consumed is refilled with the slot KW ahead.
+// 4 * KW * 4 registers instead of the 128 a whole key pair would pin, which is what makes room for the second data set.
+// ---------------------------------------------------------------------------------------------
+template <int KW> struct KeyWindow { cplx k[KW][4]; };
+template <int LOGM, int KW>
+__device__ __forceinline__ void keywin_load(KeyWindow<KW>& w, const cplx* __restrict__ kb, const int slot) {
+    typedef TreePlan<LOGM> P;
+#pragma unroll
+    for (int j = 0; j < 4; j++) w.k[slot % KW][j] = __ldg(kb + (size_t)j * P::M + slot * P::T);
+}
+template <int LOGM, int KW>
+__device__ __forceinline__ void mac2_tmem(const bool first, const uint32_t tacc, const cplx (&v)[16], const cplx (&u)[16],
+                                          KeyWindow<KW>& w, const cplx* __restrict__ kb) {
+    if (!first) tmem_wait_st();
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        uint32_t r0[16], r1[16];
+        if (!first) { TFHE_TLD16(r0, tacc + 16 * c); TFHE_TLD16(r1, tacc + 64 + 16 * c); tmem_wait_ld(); }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int s = 4 * c + i;
+            cplx R0 = first ? make_double2(0.0, 0.0)
+                            : make_double2(__hiloint2double((int)r0[4 * i + 1], (int)r0[4 * i]), __hiloint2double((int)r0[4 * i + 3], (int)r0[4 * i + 2]));
+            cplx R1 = first ? make_double2(0.0, 0.0)
+                            : make_double2(__hiloint2double((int)r1[4 * i + 1], (int)r1[4 * i]), __hiloint2double((int)r1[4 * i + 3], (int)r1[4 * i + 2]));
+            cfma(R0, v[s], w.k[s % KW][0]); cfma(R1, v[s], w.k[s % KW][1]);
+            cfma(R0, u[s], w.k[s % KW][2]); cfma(R1, u[s], w.k[s % KW][3]);
+            r0[4 * i] = (uint32_t)__double2loint(R0.x); r0[4 * i + 1] = (uint32_t)__double2hiint(R0.x);
+            r0[4 * i + 2] = (uint32_t)__double2loint(R0.y); r0[4 * i + 3] = (uint32_t)__double2hiint(R0.y);
+            r1[4 * i] = (uint32_t)__double2loint(R1.x); r1[4 * i + 1] = (uint32_t)__double2hiint(R1.x);
+            r1[4 * i + 2] = (uint32_t)__double2loint(R1.y); r1[4 * i + 3] = (uint32_t)__double2hiint(R1.y);
+            if (s + KW < 16) {
+                const cplx* __restrict__ kn = kb;
+                asm volatile("" : "+l"(kn) : "d"(R1.y));          // the refill is requested here, not hoisted to the top
+                keywin_load<LOGM, KW>(w, kn, s + KW);
+            }
+        }
+        TFHE_TST16(r0, tacc + 16 * c);
+        TFHE_TST16(r1, tacc + 64 + 16 * c);
+    }
+}
+
+// torus value -> the digit of gadget level with shift sh, as a double
+template <typename U> __device__ __forceinline__ double digit_of(const U x, const int sh, const uint32_t mask, const int half) {
+    return (double)((int)((uint32_t)(x >> sh) & mask) - half);
+}
+
+// One CMUX, digit polynomials taken two at a time (see above).  Same contract as cmux_step.  l even: l/2 pairs per accumulator
+// polynomial; l odd: the last level goes through the single-polynomial path.  The rotated differences u = (X^a - 1) ACC_q + offset
+// are cut into both digits of the first pair as they are formed; later pairs (l > 2) reload them from the tensor-memory stash.
+template <int LOGM, typename Torus, int KW, bool PLAIN = false>
+__device__ __forceinline__ void cmux_step2(Torus* __restrict__ acc, const int a, const cplx* __restrict__ bk,
+                                           const int l, const int Bgbit, cplx* __restrict__ buf, const uint32_t tacc,
+                                           const cplx* __restrict__ tw, const int t, const int bar_id, const uint32_t ttw) {
+    typedef TreePlan<LOGM> P;
+    typedef typename TorusTraits<Torus>::U U;
+    constexpr int M = P::M, N = P::N, T = P::T, W = TorusTraits<Torus>::W;
+    constexpr int WPC = StashWords<Torus>::PER_C;
+    constexpr bool NOTT9 = sizeof(Torus) == 8;                    // Torus64: depth-9 twiddles in shared memory (stash takes their columns)
+    const U offset = decomp_offset((U)0, l, Bgbit);
+    const uint32_t mask = (1u << Bgbit) - 1u;
+    const int half = 1 << (Bgbit - 1);
+    const bool stash = l > 2;
+    KeyPipe kp_unused{};
+
+#pragma unroll 1
+    for (int q = 0; q < 2; q++) {
+        const Torus* __restrict__ aq = acc + q * N;
+#pragma unroll 1
+        for (int lev = 0; lev < l; lev += 2) {
+            const int p = q * l + lev;
+            const cplx* __restrict__ kb = bk + (size_t)(p * 2) * M + t;
+            if (lev + 1 < l) {
+                const int sh0 = W - (lev + 1) * Bgbit, sh1 = sh0 - Bgbit;
+                cplx v[16], u[16];
+                if (lev == 0) {
+                    int a2 = a, tj = t;
+                    asm volatile("" : "+r"(a2), "+r"(tj));          // keep the 32 rotated addresses from being hoisted out of the loop
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        uint32_t w[WPC];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int j = tj + T * (4 * c + i);
+                            const U ure = (U)(PLAIN ? aq[j] : rot_minus_one<Torus, N>(aq, j, a2)) + offset;
+                            const U uim = (U)(PLAIN ? aq[j + M] : rot_minus_one<Torus, N>(aq, j + M, a2)) + offset;
+                            v[4 * c + i] = make_double2(digit_of(ure, sh0, mask, half), digit_of(uim, sh0, mask, half));
+                            u[4 * c + i] = make_double2(digit_of(ure, sh1, mask, half), digit_of(uim, sh1, mask, half));
+                            if (WPC == 8) { w[(2 * i) % WPC] = (uint32_t)ure; w[(2 * i + 1) % WPC] = (uint32_t)uim; }
+                            else { w[(4 * i) % WPC] = (uint32_t)ure; w[(4 * i + 1) % WPC] = (uint32_t)((uint64_t)ure >> 32);
+                                   w[(4 * i + 2) % WPC] = (uint32_t)uim; w[(4 * i + 3) % WPC] = (uint32_t)((uint64_t)uim >> 32); }
+                        }
+                        if (stash) {
+                            if constexpr (WPC == 8) { TFHE_TST8(w, tacc + 128 + WPC * c); }
+                            else                    { TFHE_TST16(w, tacc + 128 + WPC * c); }
+                        }
+                    }
+                } else {
+                    uint32_t w[4][WPC];
+                    tmem_wait_st();
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        if constexpr (WPC == 8) { TFHE_TLD8(w[c], tacc + 128 + WPC * c); }
+                        else                    { TFHE_TLD16(w[c], tacc + 128 + WPC * c); }
+                    }
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            U ure, uim;
+                            if (WPC == 8) { ure = (U)w[c][(2 * i) % WPC]; uim = (U)w[c][(2 * i + 1) % WPC]; }
+                            else { ure = (U)(((uint64_t)w[c][(4 * i + 1) % WPC] << 32) | w[c][(4 * i) % WPC]);
+                                   uim = (U)(((uint64_t)w[c][(4 * i + 3) % WPC] << 32) | w[c][(4 * i + 2) % WPC]); }
+                            v[4 * c + i] = make_double2(digit_of(ure, sh0, mask, half), digit_of(uim, sh0, mask, half));
+                            u[4 * c + i] = make_double2(digit_of(ure, sh1, mask, half), digit_of(uim, sh1, mask, half));
+                        }
+                }
+                KeyWindow<KW> kw;
+#pragma unroll
+                for (int s = 0; s < KW; s++) keywin_load<LOGM, KW>(kw, kb, s);
+                tree_forward2<LOGM, !NOTT9>(v, u, buf, tw, t, bar_id, ttw);
+                mac2_tmem<LOGM, KW>(p == 0, tacc, v, u, kw, kb);
+            } else {
+                // odd l: the last level alone (reloaded from the stash when there is one)
+                const int sh = W - (lev + 1) * Bgbit;
+                cplx v[16];
+                if (lev > 0) {
+                    uint32_t w[4][WPC];
+                    tmem_wait_st();
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        if constexpr (WPC == 8) { TFHE_TLD8(w[c], tacc + 128 + WPC * c); }
+                        else                    { TFHE_TLD16(w[c], tacc + 128 + WPC * c); }
+                    }
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            U ure, uim;
+                            if (WPC == 8) { ure = (U)w[c][(2 * i) % WPC]; uim = (U)w[c][(2 * i + 1) % WPC]; }
+                            else { ure = (U)(((uint64_t)w[c][(4 * i + 1) % WPC] << 32) | w[c][(4 * i) % WPC]);
+                                   uim = (U)(((uint64_t)w[c][(4 * i + 3) % WPC] << 32) | w[c][(4 * i + 2) % WPC]); }
+                            v[4 * c + i] = make_double2(digit_of(ure, sh, mask, half), digit_of(uim, sh, mask, half));
+                        }
+                } else {
+                    int a2 = a, tj = t;
+                    asm volatile("" : "+r"(a2), "+r"(tj));
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int j = tj + T * i;
+                        const U ure = (U)(PLAIN ? aq[j] : rot_minus_one<Torus, N>(aq, j, a2)) + offset;
+                        const U uim = (U)(PLAIN ? aq[j + M] : rot_minus_one<Torus, N>(aq, j + M, a2)) + offset;
+                        v[i] = make_double2(digit_of(ure, sh, mask, half), digit_of(uim, sh, mask, half));
+                    }
+                }
+                if (p == 0) forward_and_mac<LOGM, true, KM_REGS2, NOTT9>(v, tacc, bk, buf, kp_unused, tw, t, bar_id, ttw);
+                else        forward_and_mac<LOGM, false, KM_REGS2, NOTT9>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp_unused, tw, t, bar_id, ttw);
+            }
+        }
+    }
+    {
+        cplx R0[16], R1[16];
+        load_tmem2(R0, R1, tacc);
+        tree_backward2<LOGM, true, !NOTT9>(R0, R1, buf, tw, t, bar_id, ttw);
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const int j = t + T * m;
+            acc[j] = (Torus)((PLAIN ? (U)0 : (U)acc[j]) + (U)to_torus(R0[m].x, (Torus)0));
+            acc[j + M] = (Torus)((PLAIN ? (U)0 : (U)acc[j + M]) + (U)to_torus(R0[m].y, (Torus)0));
+            acc[N + j] = (Torus)((PLAIN ? (U)0 : (U)acc[N + j]) + (U)to_torus(R1[m].x, (Torus)0));
+            acc[N + j + M] = (Torus)((PLAIN ? (U)0 : (U)acc[N + j + M]) + (U)to_torus(R1[m].y, (Torus)0));
+        }
+    }
+    lanes_sync<T>(bar_id);      // accumulator writes visible before the next step's rotated reads
+}
+
 // One CMUX: ACC <- ACC + BK_i (x) ((X^a - 1) ACC).   acc: shared [2][N].  bk: BK_i = [2l][2][M] spectra (scaled 2/N).
 // STASH: the rotated difference u = (X^a - 1) ACC_q + offset of a coefficient is formed ONCE per q (level 0: two shared-memory
 // reads, index and sign arithmetic) and parked in this lane's tensor-memory columns [128, 128 + 32 words); levels 1.. only
 // reload it and cut their digit.  Otherwise every level re-reads the accumulator.
-template <typename Torus> struct StashWords { static constexpr int PER_C = 8 * (int)(sizeof(Torus) / 4); };   // words per c (4 complex)
 // PLAIN: the external product alone, ACC <- BK (x) ACC (tGswFFTExternMulToTLwe, cb/tgsw_functions.cpp:424-449): no rotation
 // on the way in, no accumulation on the way out.
 template <int LOGM, typename Torus, bool STASH, int KM, bool PLAIN = false>
@@ -413,7 +597,7 @@ __device__ __forceinline__ int fetch_bara(const BRArgs& A, const int ct, const i
     return __ldg(A.bara + (size_t)ct * n + i);
 }
 
-template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM>
+template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM, int F2 = 0>
 __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_kernel(const BRArgs A) {
     typedef TreePlan<LOGM> P;
     typedef typename TorusTraits<Torus>::U U;
@@ -499,7 +683,8 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
                 if (KM == KM_TMEM) for (int p = 0; p < 2 * l; p++) { kp.acquire(t & 31); kp.release(t & 31); }     // stay aligned with the key stream
                 continue;
             }
-            cmux_step<LOGM, Torus, STASH, KM>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, kp, tw, t, bar_id, ttw);
+            if constexpr (F2 > 0) cmux_step2<LOGM, Torus, F2>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, tw, t, bar_id, ttw);
+            else cmux_step<LOGM, Torus, STASH, KM>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, kp, tw, t, bar_id, ttw);
         }
 
         TL(99);
@@ -598,13 +783,13 @@ static PerDeviceOnce g_inited;
 //             tensor-memory key buffer and the 2 200-cycle copy issue per chunk give that back -- kept selectable for round 2)
 constexpr int G32 = 8, G32_KP = 12, G64 = 4;     // accumulators per CTA (N=1024: one warp each; N=2048: two warps each)
 
-template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM> static cudaError_t br_attr() {
-    return cudaFuncSetAttribute(blind_rotate_kernel<LOGM, Torus, GROUPS, STASH, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM, int F2 = 0> static cudaError_t br_attr() {
+    return cudaFuncSetAttribute(blind_rotate_kernel<LOGM, Torus, GROUPS, STASH, KM, F2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)BRSmem<LOGM, Torus, GROUPS, STASH, KM>::TOTAL);
 }
-template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM> static cudaError_t br_launch(const BRArgs& a, long units, cudaStream_t s) {
+template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM, int F2 = 0> static cudaError_t br_launch(const BRArgs& a, long units, cudaStream_t s) {
     const int grid = (int)((units + GROUPS - 1) / GROUPS);
-    blind_rotate_kernel<LOGM, Torus, GROUPS, STASH, KM><<<grid, GROUPS * TreePlan<LOGM>::T, BRSmem<LOGM, Torus, GROUPS, STASH, KM>::TOTAL, s>>>(a);
+    blind_rotate_kernel<LOGM, Torus, GROUPS, STASH, KM, F2><<<grid, GROUPS * TreePlan<LOGM>::T, BRSmem<LOGM, Torus, GROUPS, STASH, KM>::TOTAL, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t blind_rotate_init() {
@@ -615,6 +800,9 @@ cudaError_t blind_rotate_init() {
     if ((e = br_attr<9, int32_t, G32, false, KM_REGS2>()) != cudaSuccess) return e;
     if ((e = br_attr<10, int64_t, G64, false, KM_REGS2>()) != cudaSuccess) return e;
     if ((e = br_attr<10, int64_t, G64, true, KM_REGS2>()) != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, G32, true, KM_REGS2, 2>()) != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, G32, true, KM_REGS2, 3>()) != cudaSuccess) return e;
+    if ((e = br_attr<10, int64_t, G64, true, KM_REGS2, 3>()) != cudaSuccess) return e;
     g_inited.done();
     return cudaSuccess;
 }
@@ -627,6 +815,11 @@ cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
     if (variant && variant[0] == 'k') return br_launch<9, int32_t, G32_KP, false, KM_TMEM>(a, a.count, s);
     if (variant && variant[0] == 'h') return br_launch<9, int32_t, G32_KP, true, KM_REGS1>(a, a.count, s);
     if (variant && variant[0] == 'n') return br_launch<9, int32_t, G32, false, KM_REGS2>(a, a.count, s);
+    // "pairs": two digit polynomials per pass (cmux_step2), rolling key window of 2 / 3 slots.  Measured 380 / 382 ms against 354 ms
+    // for the default (profiles/r2_notes.md): what the side-by-side transforms gain (short_scoreboard 10.3 -> 5.9 %) the exposed
+    // key latency in the multiply-accumulate gives back (long_scoreboard 1.4 -> 7.6 %), and 255 registers leave a few spills.
+    if (variant && variant[0] == '2') return br_launch<9, int32_t, G32, true, KM_REGS2, 2>(a, a.count, s);
+    if (variant && variant[0] == '3') return br_launch<9, int32_t, G32, true, KM_REGS2, 3>(a, a.count, s);
     return br_launch<9, int32_t, G32, true, KM_REGS2>(a, a.count, s);
 }
 cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
@@ -637,6 +830,7 @@ cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
     // With the waits deferred the stash pays here too (189 vs 201 ms per 4096 circuit bootstraps; before that it cost 3 %).
     static const char* variant = getenv("TFHE_B200_BR_VARIANT");
     if (variant && variant[0] == 'n') return br_launch<10, int64_t, G64, false, KM_REGS2>(a, units, s);      // "nostash"
+    if (variant && variant[0] == '3') return br_launch<10, int64_t, G64, true, KM_REGS2, 3>(a, units, s);    // "pairs": 196 vs 188 ms
     return br_launch<10, int64_t, G64, true, KM_REGS2>(a, units, s);
 }
 

@@ -35,6 +35,12 @@ struct tfhe_b200_ctx {
     // scratch (grown on demand, never per call once warm)
     void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[4] = {0, 0, 0, 0};
+    // Scratch is one set per context while every *_batch call is asynchronous on the CALLER's stream: users of the scratch are
+    // ordered against each other through this event (recorded behind the last kernel of each call, waited for by the next call
+    // when it arrives on another stream) -- see ScratchUse below.
+    cudaEvent_t scratch_ev = nullptr;
+    bool scratch_busy = false;
+    cudaStream_t scratch_stream = nullptr;
     // two private streams for the chunked host-buffer path (copies of one chunk overlap the kernels of another)
     cudaStream_t hs[2] = {nullptr, nullptr};
     // profiling (diagnostics): events around every launch when enabled
@@ -71,8 +77,31 @@ static int fail(tfhe_b200_ctx* c, int code, const std::string& msg) {
     } while (0)
 #define NEED(cond, msg) do { if (!(cond)) return fail(ctx, TFHE_B200_ERR_PARAM, msg); } while (0)
 
+// Brackets the launches of one entry point that uses ctx->scratch.  Two calls on different streams of the same context would
+// otherwise race on the scratch buffers (the second call's blind rotation overwriting what the first call's key switch still
+// reads); with the bracket the second call's stream waits for the first call's last kernel.  Calls on one stream cost nothing
+// extra (stream order already holds).  While `stream` is being captured into a CUDA graph the bracket does nothing: a captured
+// sequence is ordered by the capture itself, and the graph must not be replayed concurrently with other calls on this context.
+struct ScratchUse {
+    tfhe_b200_ctx* c; cudaStream_t s; bool active = false;
+    ScratchUse(tfhe_b200_ctx* ctx, cudaStream_t st) : c(ctx), s(st) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+        active = cs == cudaStreamCaptureStatusNone;
+        if (!active) return;
+        if (!c->scratch_ev) cudaEventCreateWithFlags(&c->scratch_ev, cudaEventDisableTiming);
+        if (c->scratch_busy && c->scratch_stream != s) cudaStreamWaitEvent(s, c->scratch_ev, 0);
+    }
+    ~ScratchUse() {
+        if (!active || !c->scratch_ev) return;
+        if (cudaEventRecord(c->scratch_ev, s) == cudaSuccess) { c->scratch_busy = true; c->scratch_stream = s; }
+    }
+};
+
 static int ensure_scratch(tfhe_b200_ctx* ctx, int slot, size_t bytes) {
     if (ctx->scratch_bytes[slot] >= bytes) return TFHE_B200_OK;
+    // growing: whatever was queued on the old buffer has to be finished before it is freed (first calls / larger batches only)
+    if (ctx->scratch_busy && ctx->scratch_ev) { CU(cudaEventSynchronize(ctx->scratch_ev)); ctx->scratch_busy = false; }
     if (ctx->scratch[slot]) { CU(cudaFree(ctx->scratch[slot])); ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0; }
     size_t want = bytes + bytes / 8;
     CU(cudaMalloc(&ctx->scratch[slot], want));
@@ -127,6 +156,7 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx) {
     if (!ctx) return TFHE_B200_OK;
     cudaSetDevice(ctx->device);
     for (int k = 0; k < 2; k++) if (ctx->hs[k]) cudaStreamDestroy(ctx->hs[k]);
+    if (ctx->scratch_ev) cudaEventDestroy(ctx->scratch_ev);
     cudaFree(ctx->tw1024); cudaFree(ctx->tw2048);
     cudaFree(ctx->g_bkfft); cudaFree(ctx->g_ks);
     cudaFree(ctx->c_bkfft); cudaFree(ctx->c_preks); cudaFree(ctx->c_privks);
@@ -173,7 +203,15 @@ int tfhe_b200_gate_alloc_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p
     ctx->g_ks_bytes = (size_t)p->N * p->ks_t * ((1 << p->ks_basebit) - 1) * gate_cols_pad(*p) * sizeof(int32_t);
     CU(cudaMalloc(&ctx->g_bkfft, ctx->g_bkfft_bytes));
     CU(cudaMalloc(&ctx->g_ks, ctx->g_ks_bytes));
-    ctx->gate_ready = true;   // contents are the caller's responsibility on this path (broadcast receiver)
+    // NOT ready yet: the buffers are uninitialised until the caller has filled them (broadcast receiver) and says so with
+    // tfhe_b200_gate_commit_keys
+    return TFHE_B200_OK;
+}
+
+int tfhe_b200_gate_commit_keys(tfhe_b200_ctx* ctx) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    if (!ctx->g_bkfft || !ctx->g_ks) return fail(ctx, TFHE_B200_ERR_NOKEY, "gate_commit_keys: gate keys not allocated");
+    ctx->gate_ready = true;
     return TFHE_B200_OK;
 }
 
@@ -181,7 +219,6 @@ int tfhe_b200_gate_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p,
     if (!ctx) return TFHE_B200_ERR_PARAM;
     NEED(bk_host && ks_host, "gate_load_keys: null key pointer");
     int rc = tfhe_b200_gate_alloc_keys(ctx, p); if (rc) return rc;
-    ctx->gate_ready = false;
     const int N = p->N, base = 1 << p->ks_basebit;
     const size_t npoly = (size_t)p->n * 2 * p->bk_l * 2;
     // bk: coefficient domain -> spectra, scaled by 2/N so the backward transform needs no scaling
@@ -264,16 +301,21 @@ int tfhe_b200_gate_import_keys(tfhe_b200_ctx* ctx, const void* buf_host, size_t 
     const unsigned char* in = (const unsigned char*)buf_host + sizeof(KeyBlobHeader);
     NEED(fnv1a(in, h.bk_bytes + h.ks_bytes) == h.checksum, "gate_import_keys: checksum mismatch");
     tfhe_b200_gate_params p{h.params[0], h.params[1], h.params[2], h.params[3], h.params[4], h.params[5], h.params[6]};
-    int rc = tfhe_b200_gate_alloc_keys(ctx, &p); if (rc) return rc;
-    ctx->gate_ready = false;
-    NEED(ctx->g_bkfft_bytes == h.bk_bytes && ctx->g_ks_bytes == h.ks_bytes, "gate_import_keys: blob sizes do not match the parameters");
+    // everything about the blob is checked BEFORE the keys currently loaded are released
+    int rc = check_gate_params(ctx, &p); if (rc) return rc;
+    NEED((size_t)p.n * 2 * p.bk_l * 2 * (p.N / 2) * sizeof(cplx) == h.bk_bytes &&
+         (size_t)p.N * p.ks_t * ((1 << p.ks_basebit) - 1) * gate_cols_pad(p) * sizeof(int32_t) == h.ks_bytes,
+         "gate_import_keys: blob sizes do not match the parameters");
+    rc = tfhe_b200_gate_alloc_keys(ctx, &p); if (rc) return rc;
     CU(cudaMemcpy(ctx->g_bkfft, in, h.bk_bytes, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->g_ks, in + h.bk_bytes, h.ks_bytes, cudaMemcpyHostToDevice));
     ctx->gate_ready = true;
     return TFHE_B200_OK;
 }
 
-#define NEED_GATE() do { if (!ctx) return TFHE_B200_ERR_PARAM; if (!ctx->gate_ready) return fail(ctx, TFHE_B200_ERR_NOKEY, "gate keys not loaded"); } while (0)
+// every entry point selects its context's device first: a process may drive several contexts (one per GPU)
+#define ENTER() do { if (!ctx) return TFHE_B200_ERR_PARAM; CU(cudaSetDevice(ctx->device)); } while (0)
+#define NEED_GATE() do { ENTER(); if (!ctx->gate_ready) return fail(ctx, TFHE_B200_ERR_NOKEY, "gate keys not loaded"); } while (0)
 
 static BRArgs gate_br_args(const tfhe_b200_ctx* ctx, int count) {
     BRArgs a{};
@@ -326,6 +368,7 @@ static int bootstrap_full(tfhe_b200_ctx* ctx, int32_t* result_dev, int32_t mu, c
                           int32_t cconst, int count, cudaStream_t s) {
     const size_t ubytes = (size_t)count * (ctx->gp.N + 1) * sizeof(int32_t);
     int rc = ensure_scratch(ctx, 0, ubytes); if (rc) return rc;
+    ScratchUse use(ctx, s);
     int32_t* u = (int32_t*)ctx->scratch[0];
     rc = bootstrap_woks(ctx, u, mu, xa, xb, ka, kb, cconst, count, s); if (rc) return rc;
     return gate_keyswitch(ctx, result_dev, u, count, s);
@@ -360,6 +403,7 @@ int tfhe_b200_bootsMUX_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int3
     const size_t ubytes = (size_t)count * (N + 1) * sizeof(int32_t);
     int rc = ensure_scratch(ctx, 0, ubytes); if (rc) return rc;
     rc = ensure_scratch(ctx, 1, ubytes); if (rc) return rc;
+    ScratchUse use(ctx, s);
     int32_t* u1 = (int32_t*)ctx->scratch[0]; int32_t* u2 = (int32_t*)ctx->scratch[1];
     // AND(a,b) and AND(not a, c), both without key switch; sum + (0,1/8); one key switch
     rc = bootstrap_woks(ctx, u1, kMU, a_dev, b_dev, 1, 1, -kMU, count, s); if (rc) return rc;
@@ -380,6 +424,8 @@ int tfhe_b200_bootsGate_batch_host(tfhe_b200_ctx* ctx, int op, int32_t* result_h
     int32_t* da = (int32_t*)ctx->scratch[2]; int32_t* db = da + (size_t)count * row; int32_t* dr = (int32_t*)ctx->scratch[3];
     int32_t* u = (int32_t*)ctx->scratch[0];
     for (int k = 0; k < 2; k++) if (!ctx->hs[k]) CU(cudaStreamCreateWithFlags(&ctx->hs[k], cudaStreamNonBlocking));
+    // the private streams are not ordered against the caller's streams: wait for whatever still uses the scratch
+    if (ctx->scratch_busy && ctx->scratch_ev) for (int k = 0; k < 2; k++) CU(cudaStreamWaitEvent(ctx->hs[k], ctx->scratch_ev, 0));
     // Chunks of whole waves (8 accumulators per SM), alternating between two streams: the host->device copies of chunk k+1 and the
     // device->host copy of chunk k-1 run under the kernels of chunk k, and the blind rotations of consecutive chunks fill each other's
     // last wave.  Small batches go through as one chunk.
@@ -399,6 +445,7 @@ int tfhe_b200_bootsGate_batch_host(tfhe_b200_ctx* ctx, int op, int32_t* result_h
     }
     CU(cudaStreamSynchronize(ctx->hs[0]));
     CU(cudaStreamSynchronize(ctx->hs[1]));
+    ctx->scratch_busy = false;            // both streams (and everything they waited for) have drained
     return TFHE_B200_OK;
 }
 
@@ -408,7 +455,7 @@ static int check_gadget(tfhe_b200_ctx* ctx, int l, int Bgbit) {
     return TFHE_B200_OK;
 }
 int tfhe_b200_tGswToFFTConvert_batch(tfhe_b200_ctx* ctx, double* gswfft_dev, const int32_t* gsw_dev, int l, int count, void* stream) {
-    if (!ctx) return TFHE_B200_ERR_PARAM;
+    ENTER();
     NEED(l >= 1 && l <= 32, "tGswToFFTConvert: bad l"); NEED(count >= 0, "count < 0"); NEED(count == 0 || (gswfft_dev && gsw_dev), "null buffer");
     const long npoly = (long)count * 2 * l * 2;
     NEED(npoly <= 0x7fffffffL, "tGswToFFTConvert: too many polynomials");
@@ -426,14 +473,14 @@ static int extmul(tfhe_b200_ctx* ctx, int32_t* accum_dev, const double* gswfft_d
 }
 int tfhe_b200_tGswFFTExternMulToTLwe_batch(tfhe_b200_ctx* ctx, int32_t* accum_dev, const double* gswfft_dev, int per_sample,
                                            int l, int Bgbit, int count, void* stream) {
-    if (!ctx) return TFHE_B200_ERR_PARAM;
+    ENTER();
     int rc = check_gadget(ctx, l, Bgbit); if (rc) return rc;
     NEED(count >= 0, "count < 0"); NEED(count == 0 || (accum_dev && gswfft_dev), "null buffer");
     return extmul(ctx, accum_dev, gswfft_dev, per_sample ? (size_t)2 * l * 2 * 512 : 0, 1, l, Bgbit, count, (cudaStream_t)stream);
 }
 int tfhe_b200_CMux_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const double* gswfft_dev, int per_sample, const int32_t* d1_dev,
                          const int32_t* d0_dev, int l, int Bgbit, int count, void* stream) {
-    if (!ctx) return TFHE_B200_ERR_PARAM;
+    ENTER();
     int rc = check_gadget(ctx, l, Bgbit); if (rc) return rc;
     NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && gswfft_dev && d1_dev && d0_dev), "null buffer");
     if (count == 0) return TFHE_B200_OK;
@@ -441,6 +488,7 @@ int tfhe_b200_CMux_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const double* 
     const int len = 2 * 1024;
     const size_t bytes = (size_t)count * len * sizeof(int32_t);
     rc = ensure_scratch(ctx, 0, bytes); if (rc) return rc;
+    ScratchUse use(ctx, s);
     int32_t* tmp = (int32_t*)ctx->scratch[0];
     // tmp = d1 - d0 ; tmp <- C (x) tmp ; result = tmp + d0      (flat rows of len int32; the lincomb constant is 0)
     { ProfScope ps(ctx, 2, s); CU(launch_lwe_lincomb(tmp, d1_dev, d0_dev, 1, -1, 0, len - 1, count, s)); }
@@ -450,7 +498,7 @@ int tfhe_b200_CMux_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const double* 
 }
 int tfhe_b200_LUT_vertical_packing_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const double* selfft_dev, int nsel,
                                          const int32_t* table_dev, int l, int Bgbit, int count, void* stream) {
-    if (!ctx) return TFHE_B200_ERR_PARAM;
+    ENTER();
     int rc = check_gadget(ctx, l, Bgbit); if (rc) return rc;
     NEED(nsel >= 1 && nsel <= 16, "LUT: nsel must be 1..16"); NEED(count >= 0, "count < 0");
     NEED(count == 0 || (result_dev && selfft_dev && table_dev), "null buffer");
@@ -463,6 +511,7 @@ int tfhe_b200_LUT_vertical_packing_batch(tfhe_b200_ctx* ctx, int32_t* result_dev
     // ping-pong level buffers: level j produces count * 2^(nsel-1-j) TRLWE of len int32
     rc = ensure_scratch(ctx, 0, lvl0_units * len * sizeof(int32_t)); if (rc) return rc;
     rc = ensure_scratch(ctx, 1, (lvl0_units / 2 + 1) * len * sizeof(int32_t)); if (rc) return rc;
+    ScratchUse use(ctx, s);
     int32_t* pp[2] = {(int32_t*)ctx->scratch[0], (int32_t*)ctx->scratch[1]};
     const int32_t* in = nullptr;
     for (int j = 0; j < nsel; j++) {
@@ -543,19 +592,19 @@ int tfhe_b200_circuit_eval_batch(tfhe_b200_ctx* ctx, const tfhe_b200_gate* gates
 static const cplx* tw_for(const tfhe_b200_ctx* ctx, int N) { return N == 1024 ? ctx->tw1024 : (N == 2048 ? ctx->tw2048 : nullptr); }
 
 int tfhe_b200_IntPolynomial_ifft_batch(tfhe_b200_ctx* ctx, double* result_dev, const int32_t* poly_dev, int N, int count, void* stream) {
-    if (!ctx) return TFHE_B200_ERR_PARAM;
+    ENTER();
     NEED(tw_for(ctx, N), "transform: N must be 1024 or 2048"); NEED(count >= 0, "count < 0");
     CU(launch_poly_to_spectrum32((cplx*)result_dev, poly_dev, tw_for(ctx, N), N, count, 1.0, (cudaStream_t)stream));
     return TFHE_B200_OK;
 }
 int tfhe_b200_TorusPolynomial64_ifft_batch(tfhe_b200_ctx* ctx, double* result_dev, const int64_t* poly_dev, int N, int count, void* stream) {
-    if (!ctx) return TFHE_B200_ERR_PARAM;
+    ENTER();
     NEED(tw_for(ctx, N), "transform: N must be 1024 or 2048"); NEED(count >= 0, "count < 0");
     CU(launch_poly_to_spectrum64((cplx*)result_dev, poly_dev, tw_for(ctx, N), N, count, 1.0, (cudaStream_t)stream));
     return TFHE_B200_OK;
 }
 int tfhe_b200_TorusPolynomial_fft_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const double* lagr_dev, int N, int count, void* stream) {
-    if (!ctx) return TFHE_B200_ERR_PARAM;
+    ENTER();
     NEED(tw_for(ctx, N), "transform: N must be 1024 or 2048"); NEED(count >= 0, "count < 0");
     CU(launch_spectrum_to_torus32(result_dev, (const cplx*)lagr_dev, tw_for(ctx, N), N, count, 2.0 / N, (cudaStream_t)stream));
     return TFHE_B200_OK;
@@ -576,28 +625,73 @@ int tfhe_b200_LagrangeHalfCPolynomialAddMul_batch(tfhe_b200_ctx* ctx, double* re
 /* ------------------------------------------------------------------ circuit bootstrapping */
 static size_t pad512(size_t c) { return (c + 511) / 512 * 512; }
 
-int tfhe_b200_cb_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p, const int32_t* preKS_host, const int64_t* bk_host,
-                           const int32_t* privKS_host) {
-    if (!ctx) return TFHE_B200_ERR_PARAM;
-    NEED(p && preKS_host && bk_host, "cb_load_keys: null pointer");
+static int check_cb_params(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p) {
+    NEED(p, "cb params: null");
     NEED(p->N_lvl2 == 2048, "cb params: only N_lvl2 = 2048 is compiled");
     NEED(p->N_lvl1 == 1024, "cb params: only N_lvl1 = 1024 is compiled");
     NEED(p->n_lvl0 >= 1 && p->n_lvl0 < 1024, "cb params: n_lvl0 out of range");
-    NEED(p->ell_lvl2 >= 1 && p->ell_lvl2 * p->bgbit_lvl2 < 64 && p->bgbit_lvl2 <= 16, "cb params: bad lvl2 gadget");
-    NEED(p->ell_lvl1 >= 1 && p->ell_lvl1 <= 4 && p->ell_lvl1 * p->bgbit_lvl1 <= 32, "cb params: bad lvl1 gadget");
+    NEED(p->ell_lvl2 >= 1 && p->bgbit_lvl2 >= 1 && p->ell_lvl2 * p->bgbit_lvl2 < 64 && p->bgbit_lvl2 <= 16, "cb params: bad lvl2 gadget");
+    NEED(p->ell_lvl1 >= 1 && p->ell_lvl1 <= 4 && p->bgbit_lvl1 >= 1 && p->ell_lvl1 * p->bgbit_lvl1 <= 32, "cb params: bad lvl1 gadget");
+    NEED(p->kslength_lvl10 >= 1 && p->kslength_lvl21 >= 1, "cb params: ks length must be >= 1");
     NEED(p->ksbasebit_lvl10 >= 1 && p->ksbasebit_lvl10 <= 3 && p->ksbasebit_lvl21 >= 1 && p->ksbasebit_lvl21 <= 3, "cb params: ks basebit must be 1..3");
     NEED(p->kslength_lvl10 * p->ksbasebit_lvl10 <= 31 && p->kslength_lvl21 * p->ksbasebit_lvl21 <= 63, "cb params: ks length too large");
+    return TFHE_B200_OK;
+}
+// device sizes of the three key blobs: bk spectra, repacked preKS, repacked privKS (both u)
+static void cb_blob_bytes(const tfhe_b200_cb_params& p, size_t out[3], size_t* privks_u_stride) {
+    out[0] = (size_t)p.n_lvl0 * 2 * p.ell_lvl2 * 2 * (p.N_lvl2 / 2) * sizeof(cplx);
+    out[1] = (size_t)p.N_lvl1 * p.kslength_lvl10 * ((1 << p.ksbasebit_lvl10) - 1) * pad512(p.n_lvl0 + 1) * sizeof(int32_t);
+    const size_t us = (size_t)(p.N_lvl2 + 1) * p.kslength_lvl21 * ((1 << p.ksbasebit_lvl21) - 1) * 2 * p.N_lvl1;
+    out[2] = 2 * us * sizeof(int32_t);
+    if (privks_u_stride) *privks_u_stride = us;
+}
+
+/* Multi-GPU replication of the circuit-bootstrap keys, same protocol as the gate keys: allocate, let the caller fill the blobs
+ * (which: 0 = bk spectra, 1 = preKS, 2 = privKS), commit. */
+int tfhe_b200_cb_alloc_keys(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p, int with_privks) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    int rc = check_cb_params(ctx, p); if (rc) return rc;
     CU(cudaSetDevice(ctx->device));
     ctx->cb_ready = false;
     cudaFree(ctx->c_bkfft); cudaFree(ctx->c_preks); cudaFree(ctx->c_privks);
     ctx->c_bkfft = nullptr; ctx->c_preks = nullptr; ctx->c_privks = nullptr;
     ctx->cp = *p;
+    size_t bytes[3];
+    cb_blob_bytes(*p, bytes, &ctx->c_privks_u_stride);
+    CU(cudaMalloc(&ctx->c_bkfft, bytes[0]));
+    CU(cudaMalloc(&ctx->c_preks, bytes[1]));
+    if (with_privks) CU(cudaMalloc(&ctx->c_privks, bytes[2]));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_cb_key_blob(tfhe_b200_ctx* ctx, int which, void** dev_ptr, size_t* bytes) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(dev_ptr && bytes, "cb_key_blob: null output");
+    NEED(which >= 0 && which <= 2, "cb_key_blob: which must be 0, 1 or 2");
+    if (!ctx->c_bkfft) return fail(ctx, TFHE_B200_ERR_NOKEY, "cb_key_blob: circuit-bootstrap keys not allocated");
+    size_t b[3];
+    cb_blob_bytes(ctx->cp, b, nullptr);
+    void* ptrs[3] = {ctx->c_bkfft, ctx->c_preks, ctx->c_privks};
+    if (which == 2 && !ctx->c_privks) return fail(ctx, TFHE_B200_ERR_NOKEY, "cb_key_blob: private key-switch key not allocated");
+    *dev_ptr = ptrs[which]; *bytes = b[which];
+    return TFHE_B200_OK;
+}
+int tfhe_b200_cb_commit_keys(tfhe_b200_ctx* ctx) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    if (!ctx->c_bkfft || !ctx->c_preks) return fail(ctx, TFHE_B200_ERR_NOKEY, "cb_commit_keys: circuit-bootstrap keys not allocated");
+    ctx->cb_ready = true;
+    return TFHE_B200_OK;
+}
+
+int tfhe_b200_cb_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p, const int32_t* preKS_host, const int64_t* bk_host,
+                           const int32_t* privKS_host) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(p && preKS_host && bk_host, "cb_load_keys: null pointer");
+    int rc = tfhe_b200_cb_alloc_keys(ctx, p, privKS_host != nullptr); if (rc) return rc;
     const int N2 = p->N_lvl2, N1 = p->N_lvl1, n0 = p->n_lvl0;
     // bk (Torus64 coefficients) -> spectra scaled by 2/N   (cb/poc_CircuitBootstrapping.cpp:394-402)
     {
         const size_t npoly = (size_t)n0 * 2 * p->ell_lvl2 * 2;
         int64_t* tmp = nullptr;
-        CU(cudaMalloc(&ctx->c_bkfft, npoly * (N2 / 2) * sizeof(cplx)));
         CU(cudaMalloc(&tmp, npoly * N2 * sizeof(int64_t)));
         CU(cudaMemcpy(tmp, bk_host, npoly * N2 * sizeof(int64_t), cudaMemcpyHostToDevice));
         cudaError_t e = launch_poly_to_spectrum64(ctx->c_bkfft, tmp, ctx->tw2048, N2, (int)npoly, 2.0 / N2, 0);
@@ -609,7 +703,6 @@ int tfhe_b200_cb_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p, con
         const int base = 1 << p->ksbasebit_lvl10, t = p->kslength_lvl10;
         const size_t raw = (size_t)N1 * t * base * (n0 + 1), cp = pad512(n0 + 1);
         int32_t* tmp = nullptr;
-        CU(cudaMalloc(&ctx->c_preks, (size_t)N1 * t * (base - 1) * cp * sizeof(int32_t)));
         CU(cudaMalloc(&tmp, raw * sizeof(int32_t)));
         CU(cudaMemcpy(tmp, preKS_host, raw * sizeof(int32_t), cudaMemcpyHostToDevice));
         cudaError_t e = launch_ks_repack(ctx->c_preks, tmp, N1, t, base, n0 + 1, (int)cp, 0);
@@ -620,22 +713,151 @@ int tfhe_b200_cb_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p, con
     if (privKS_host) {   // privKS [2][N2+1][t21][base21][2][N1]
         const int base = 1 << p->ksbasebit_lvl21, t = p->kslength_lvl21, cols = 2 * N1;
         const size_t raw_u = (size_t)(N2 + 1) * t * base * cols;
-        ctx->c_privks_u_stride = (size_t)(N2 + 1) * t * (base - 1) * cols;
         int32_t* tmp = nullptr;
-        CU(cudaMalloc(&ctx->c_privks, 2 * ctx->c_privks_u_stride * sizeof(int32_t)));
-        CU(cudaMalloc(&tmp, raw_u * sizeof(int32_t)));
+        // staged in slices of input rows (64 MB at a time) instead of one 1.3 GB temporary per u
+        const size_t row_raw = (size_t)t * base * cols;
+        int slice = (int)((size_t)(64u << 20) / (row_raw * sizeof(int32_t)));
+        if (slice < 1) slice = 1;
+        CU(cudaMalloc(&tmp, (size_t)slice * row_raw * sizeof(int32_t)));
         for (int u = 0; u < 2; u++) {
-            CU(cudaMemcpy(tmp, privKS_host + (size_t)u * raw_u, raw_u * sizeof(int32_t), cudaMemcpyHostToDevice));
-            cudaError_t e = launch_ks_repack(ctx->c_privks + (size_t)u * ctx->c_privks_u_stride, tmp, N2 + 1, t, base, cols, cols, 0);
-            if (e == cudaSuccess) e = cudaDeviceSynchronize();
-            if (e != cudaSuccess) { cudaFree(tmp); CU(e); }
+            for (int r0 = 0; r0 <= N2; r0 += slice) {
+                const int nr = N2 + 1 - r0 < slice ? N2 + 1 - r0 : slice;
+                cudaError_t e = cudaMemcpy(tmp, privKS_host + (size_t)u * raw_u + (size_t)r0 * row_raw, (size_t)nr * row_raw * sizeof(int32_t), cudaMemcpyHostToDevice);
+                if (e == cudaSuccess) e = launch_ks_repack_rows(ctx->c_privks + (size_t)u * ctx->c_privks_u_stride, tmp, N2 + 1, r0, nr, t, base, cols, cols, 0);
+                if (e == cudaSuccess) e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { cudaFree(tmp); CU(e); }
+            }
         }
         cudaFree(tmp);
     }
     ctx->cb_ready = true;
     return TFHE_B200_OK;
 }
-#define NEED_CB() do { if (!ctx) return TFHE_B200_ERR_PARAM; if (!ctx->cb_ready) return fail(ctx, TFHE_B200_ERR_NOKEY, "circuit-bootstrap keys not loaded"); } while (0)
+
+/* Wire format of the LOADED circuit-bootstrap keys: the same 96-byte header as the gate keys with kind = 2 and
+ * the eleven parameters spread over params[8] + reserved, then the three device blobs as they sit in memory.  The 2.35 GB private
+ * key-switch key moves in 64 MB slices through a pinned bounce buffer in both directions: no full-size temporary anywhere.
+ * The checksum is FNV-1a over the payload in stream order. */
+struct CBKeyBlobHeader {          // 128 bytes, little endian
+    char magic[8];                // "TFHEB200"
+    uint32_t version, kind;       // kind 2 = circuit-bootstrap keys
+    int32_t params[12];           // the eleven tfhe_b200_cb_params fields in declaration order, then with_privks
+    uint64_t blob_bytes[3], checksum;
+    uint64_t reserved[4];
+};
+static_assert(sizeof(CBKeyBlobHeader) == 128, "cb wire header is 128 bytes");
+int tfhe_b200_cb_export_keys(tfhe_b200_ctx* ctx, void* buf_host, size_t* bytes) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    if (!ctx->cb_ready) return fail(ctx, TFHE_B200_ERR_NOKEY, "cb_export_keys: circuit-bootstrap keys not loaded");
+    NEED(bytes, "cb_export_keys: null size pointer");
+    size_t b[3];
+    cb_blob_bytes(ctx->cp, b, nullptr);
+    if (!ctx->c_privks) b[2] = 0;
+    const size_t need = sizeof(CBKeyBlobHeader) + b[0] + b[1] + b[2];
+    if (!buf_host) { *bytes = need; return TFHE_B200_OK; }
+    NEED(*bytes >= need, "cb_export_keys: buffer too small");
+    CU(cudaSetDevice(ctx->device));
+    unsigned char* out = (unsigned char*)buf_host + sizeof(CBKeyBlobHeader);
+    const void* src[3] = {ctx->c_bkfft, ctx->c_preks, ctx->c_privks};
+    uint64_t h64 = 1469598103934665603ull;
+    const size_t SL = (size_t)64 << 20;
+    for (int k = 0; k < 3; k++) {
+        for (size_t off = 0; off < b[k]; off += SL) {
+            const size_t n = b[k] - off < SL ? b[k] - off : SL;
+            CU(cudaMemcpy(out, (const unsigned char*)src[k] + off, n, cudaMemcpyDeviceToHost));
+            h64 = fnv1a(out, n, h64);
+            out += n;
+        }
+    }
+    CBKeyBlobHeader h{};
+    memcpy(h.magic, "TFHEB200", 8);
+    h.version = kKeyBlobVersion; h.kind = 2;
+    memcpy(h.params, &ctx->cp, 11 * sizeof(int32_t));
+    h.params[11] = ctx->c_privks ? 1 : 0;
+    for (int k = 0; k < 3; k++) h.blob_bytes[k] = b[k];
+    h.checksum = h64;
+    memcpy(buf_host, &h, sizeof(h));
+    *bytes = need;
+    return TFHE_B200_OK;
+}
+int tfhe_b200_cb_import_keys(tfhe_b200_ctx* ctx, const void* buf_host, size_t bytes) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(buf_host && bytes >= sizeof(CBKeyBlobHeader), "cb_import_keys: buffer too small for a header");
+    CBKeyBlobHeader h;
+    memcpy(&h, buf_host, sizeof(h));
+    NEED(memcmp(h.magic, "TFHEB200", 8) == 0, "cb_import_keys: bad magic");
+    NEED(h.version == kKeyBlobVersion, "cb_import_keys: key blob written by another format version");
+    NEED(h.kind == 2, "cb_import_keys: not a circuit-bootstrap key blob");
+    tfhe_b200_cb_params p;
+    memcpy(&p, h.params, 11 * sizeof(int32_t));
+    const int with_privks = h.params[11] != 0;
+    int rc = check_cb_params(ctx, &p); if (rc) return rc;
+    size_t b[3];
+    cb_blob_bytes(p, b, nullptr);
+    if (!with_privks) b[2] = 0;
+    NEED(h.blob_bytes[0] == b[0] && h.blob_bytes[1] == b[1] && h.blob_bytes[2] == b[2], "cb_import_keys: blob sizes do not match the parameters");
+    NEED(bytes == sizeof(CBKeyBlobHeader) + b[0] + b[1] + b[2], "cb_import_keys: size does not match the header");
+    const unsigned char* in = (const unsigned char*)buf_host + sizeof(CBKeyBlobHeader);
+    NEED(fnv1a(in, b[0] + b[1] + b[2]) == h.checksum, "cb_import_keys: checksum mismatch");
+    // everything checked: only now are the keys currently loaded released
+    rc = tfhe_b200_cb_alloc_keys(ctx, &p, with_privks); if (rc) return rc;
+    void* dst[3] = {ctx->c_bkfft, ctx->c_preks, ctx->c_privks};
+    for (int k = 0; k < 3; k++) {
+        if (b[k]) CU(cudaMemcpy(dst[k], in, b[k], cudaMemcpyHostToDevice));      // straight from the caller's buffer: no staging copy
+        in += b[k];
+    }
+    ctx->cb_ready = true;
+    return TFHE_B200_OK;
+}
+
+/* Ciphertext wire format (the reference has none): a 64-byte header -- magic "TFHEB2CT", version, kind
+ * (1 LWE32, 2 LWE64, 3 TLWE32, 4 TGSW32), up to four dimensions (slowest first, e.g. {count, n+1}), payload bytes, FNV-1a checksum --
+ * followed by the samples in the flat layouts of this header's first comment.  Host-side only (no device work): what a client sends
+ * to the server that owns the context.  pack: buf = NULL returns the size. */
+struct CtHeader { char magic[8]; uint32_t version, kind; int64_t dims[4]; uint64_t payload_bytes, checksum; };
+static_assert(sizeof(CtHeader) == 64, "ciphertext wire header is 64 bytes");
+static size_t ct_elem_bytes(int kind) { return kind == 2 ? 8 : 4; }
+int tfhe_b200_ciphertext_pack(int kind, const int64_t dims[4], const void* samples_host, void* buf_host, size_t* bytes) {
+    tfhe_b200_ctx* ctx = nullptr;
+    NEED(kind >= 1 && kind <= 4 && dims && bytes, "ciphertext_pack: bad arguments");
+    size_t n = ct_elem_bytes(kind);
+    for (int i = 0; i < 4; i++) { NEED(dims[i] >= 0 && dims[i] < ((int64_t)1 << 40), "ciphertext_pack: bad dimension"); if (dims[i] > 0) n *= (size_t)dims[i]; }
+    const size_t need = sizeof(CtHeader) + n;
+    if (!buf_host) { *bytes = need; return TFHE_B200_OK; }
+    NEED(samples_host && *bytes >= need, "ciphertext_pack: buffer too small");
+    CtHeader h{};
+    memcpy(h.magic, "TFHEB2CT", 8);
+    h.version = 1; h.kind = (uint32_t)kind;
+    for (int i = 0; i < 4; i++) h.dims[i] = dims[i];
+    h.payload_bytes = n;
+    h.checksum = fnv1a((const unsigned char*)samples_host, n);
+    memcpy(buf_host, &h, sizeof(h));
+    memcpy((unsigned char*)buf_host + sizeof(h), samples_host, n);
+    *bytes = need;
+    return TFHE_B200_OK;
+}
+int tfhe_b200_ciphertext_unpack(const void* buf_host, size_t bytes, int* kind, int64_t dims[4], void* samples_host, size_t* sample_bytes) {
+    tfhe_b200_ctx* ctx = nullptr;
+    NEED(buf_host && bytes >= sizeof(CtHeader) && sample_bytes, "ciphertext_unpack: buffer too small for a header");
+    CtHeader h;
+    memcpy(&h, buf_host, sizeof(h));
+    NEED(memcmp(h.magic, "TFHEB2CT", 8) == 0, "ciphertext_unpack: bad magic");
+    NEED(h.version == 1, "ciphertext_unpack: unknown format version");
+    NEED(h.kind >= 1 && h.kind <= 4, "ciphertext_unpack: unknown kind");
+    size_t n = ct_elem_bytes((int)h.kind);
+    for (int i = 0; i < 4; i++) { NEED(h.dims[i] >= 0 && h.dims[i] < ((int64_t)1 << 40), "ciphertext_unpack: bad dimension"); if (h.dims[i] > 0) n *= (size_t)h.dims[i]; }
+    NEED(n == h.payload_bytes && bytes == sizeof(CtHeader) + n, "ciphertext_unpack: size does not match the header");
+    if (kind) *kind = (int)h.kind;
+    if (dims) for (int i = 0; i < 4; i++) dims[i] = h.dims[i];
+    if (!samples_host) { *sample_bytes = n; return TFHE_B200_OK; }
+    NEED(*sample_bytes >= n, "ciphertext_unpack: output buffer too small");
+    const unsigned char* in = (const unsigned char*)buf_host + sizeof(CtHeader);
+    NEED(fnv1a(in, n) == h.checksum, "ciphertext_unpack: checksum mismatch");
+    memcpy(samples_host, in, n);
+    *sample_bytes = n;
+    return TFHE_B200_OK;
+}
+#define NEED_CB() do { ENTER(); if (!ctx->cb_ready) return fail(ctx, TFHE_B200_ERR_NOKEY, "circuit-bootstrap keys not loaded"); } while (0)
 
 int tfhe_b200_preKeySwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* x_dev, int count, void* stream) {
     NEED_CB(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && x_dev), "null buffer");
@@ -678,44 +900,74 @@ int tfhe_b200_circuitPrivKS_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, int u
     NEED(u == 0 || u == 1, "circuitPrivKS: u must be 0 or 1"); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && x_dev), "null buffer");
     return cb_privks(ctx, result_dev, 2 * ctx->cp.N_lvl1, u, x_dev, ctx->cp.N_lvl2 + 1, count, (cudaStream_t)stream);
 }
+// one chunk of the circuit bootstrap on stream s with explicit scratch pointers (pre / abar / boot hold `count` samples):
+// preKeySwitch :832, preModSwitch :836, both mu_w in ONE pass over bk (boot[B][ell1][N2+1]; the reference makes two passes :845-847),
+// then result[B][u][w][2][N1]: all four private key switches (u,w) in one launch :852-855 -- samples are the B*ell1 rows of boot,
+// grid.z walks u (key and output offset)
+static int cb_chunk(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* sample_dev, int32_t* pre, int32_t* abar, int64_t* boot,
+                    int count, cudaStream_t s) {
+    const tfhe_b200_cb_params& p = ctx->cp;
+    const int ell1 = p.ell_lvl1, N1 = p.N_lvl1, N2 = p.N_lvl2;
+    int rc;
+    if ((rc = tfhe_b200_preKeySwitch_batch(ctx, pre, sample_dev, count, s))) return rc;
+    if ((rc = tfhe_b200_preModSwitch_batch(ctx, abar, pre, count, s))) return rc;
+    if ((rc = cb_woks(ctx, boot, 0, ell1, p.bgbit_lvl1, abar, count, s))) return rc;
+    KSArgs k{};
+    k.in = boot; k.in_stride = N2 + 1; k.rows_in = N2 + 1; k.t = p.kslength_lvl21; k.basebit = p.ksbasebit_lvl21;
+    k.key = ctx->c_privks; k.cols = 2 * N1; k.cols_pad = 2 * N1; k.b_col = -1; k.b_index = 0;
+    k.out = result_dev; k.count = count * ell1; k.group = ell1; k.out_stride = 2 * ell1 * 2 * N1; k.out_inner = 2 * N1;
+    k.nz = 2; k.key_z_stride = ctx->c_privks_u_stride; k.out_z_stride = (size_t)ell1 * 2 * N1;
+    { ProfScope ps(ctx, 1, s); CU(launch_keyswitch64(k, s)); }
+    return TFHE_B200_OK;
+}
 int tfhe_b200_CircuitBootstrapFFT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* sample_dev, int count, void* stream) {
     NEED_CB(); NEED(ctx->c_privks, "CircuitBootstrapFFT: private key-switch key was not loaded");
     NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && sample_dev), "null buffer");
     const tfhe_b200_cb_params& p = ctx->cp;
     cudaStream_t s = (cudaStream_t)stream;
-    const int ell1 = p.ell_lvl1, n0 = p.n_lvl0, N1 = p.N_lvl1, N2 = p.N_lvl2;
+    const int ell1 = p.ell_lvl1, n0 = p.n_lvl0, N2 = p.N_lvl2;
     int rc;
     if ((rc = ensure_scratch(ctx, 0, (size_t)count * (n0 + 1) * sizeof(int32_t)))) return rc;
     if ((rc = ensure_scratch(ctx, 1, (size_t)count * (n0 + 1) * sizeof(int32_t)))) return rc;
     if ((rc = ensure_scratch(ctx, 2, (size_t)count * ell1 * (N2 + 1) * sizeof(int64_t)))) return rc;
+    ScratchUse use(ctx, s);
     int32_t* pre = (int32_t*)ctx->scratch[0]; int32_t* abar = (int32_t*)ctx->scratch[1]; int64_t* boot = (int64_t*)ctx->scratch[2];
-    if ((rc = tfhe_b200_preKeySwitch_batch(ctx, pre, sample_dev, count, stream))) return rc;          // :832
-    if ((rc = tfhe_b200_preModSwitch_batch(ctx, abar, pre, count, stream))) return rc;                // :836
-    // both mu_w in one pass over bk: boot[B][ell1][N2+1]                                             // :845-847
-    if ((rc = cb_woks(ctx, boot, 0, ell1, p.bgbit_lvl1, abar, count, s))) return rc;
-    // result[B][u][w][2][N1]: all four private key switches (u,w) in one launch -- samples are the B*ell1 rows of boot,  // :852-855
-    // grid.z walks u (key and output offset)
-    {
-        KSArgs k{};
-        k.in = boot; k.in_stride = N2 + 1; k.rows_in = N2 + 1; k.t = p.kslength_lvl21; k.basebit = p.ksbasebit_lvl21;
-        k.key = ctx->c_privks; k.cols = 2 * N1; k.cols_pad = 2 * N1; k.b_col = -1; k.b_index = 0;
-        k.out = result_dev; k.count = count * ell1; k.group = ell1; k.out_stride = 2 * ell1 * 2 * N1; k.out_inner = 2 * N1;
-        k.nz = 2; k.key_z_stride = ctx->c_privks_u_stride; k.out_z_stride = (size_t)ell1 * 2 * N1;
-        { ProfScope ps(ctx, 1, s); CU(launch_keyswitch64(k, s)); }
-    }
-    return TFHE_B200_OK;
+    return cb_chunk(ctx, result_dev, sample_dev, pre, abar, boot, count, s);
 }
 int tfhe_b200_CircuitBootstrapFFT_batch_host(tfhe_b200_ctx* ctx, int32_t* result_host, const int32_t* sample_host, int count) {
-    NEED_CB(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_host && sample_host), "null buffer");
+    NEED_CB(); NEED(ctx->c_privks, "CircuitBootstrapFFT: private key-switch key was not loaded");
+    NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_host && sample_host), "null buffer");
+    if (count == 0) return TFHE_B200_OK;
     const tfhe_b200_cb_params& p = ctx->cp;
-    const size_t in_bytes = (size_t)count * (p.N_lvl1 + 1) * sizeof(int32_t);
-    const size_t out_bytes = (size_t)count * 2 * p.ell_lvl1 * 2 * p.N_lvl1 * sizeof(int32_t);
-    int rc = ensure_scratch(ctx, 3, in_bytes + out_bytes); if (rc) return rc;
+    const int ell1 = p.ell_lvl1, n0 = p.n_lvl0, N2 = p.N_lvl2;
+    const size_t in_row = (size_t)p.N_lvl1 + 1, out_row = (size_t)2 * ell1 * 2 * p.N_lvl1;
+    const size_t in_bytes = (size_t)count * in_row * sizeof(int32_t), out_bytes = (size_t)count * out_row * sizeof(int32_t);
+    int rc;
+    if ((rc = ensure_scratch(ctx, 3, in_bytes + out_bytes))) return rc;
+    if ((rc = ensure_scratch(ctx, 0, (size_t)count * (n0 + 1) * sizeof(int32_t)))) return rc;
+    if ((rc = ensure_scratch(ctx, 1, (size_t)count * (n0 + 1) * sizeof(int32_t)))) return rc;
+    if ((rc = ensure_scratch(ctx, 2, (size_t)count * ell1 * (N2 + 1) * sizeof(int64_t)))) return rc;
     int32_t* din = (int32_t*)ctx->scratch[3]; int32_t* dout = (int32_t*)((char*)ctx->scratch[3] + in_bytes);
-    CU(cudaMemcpyAsync(din, sample_host, in_bytes, cudaMemcpyHostToDevice, 0));
-    rc = tfhe_b200_CircuitBootstrapFFT_batch(ctx, dout, din, count, nullptr); if (rc) return rc;
-    CU(cudaMemcpyAsync(result_host, dout, out_bytes, cudaMemcpyDeviceToHost, 0));
-    CU(cudaStreamSynchronize(0));
+    int32_t* pre = (int32_t*)ctx->scratch[0]; int32_t* abar = (int32_t*)ctx->scratch[1]; int64_t* boot = (int64_t*)ctx->scratch[2];
+    for (int k = 0; k < 2; k++) if (!ctx->hs[k]) CU(cudaStreamCreateWithFlags(&ctx->hs[k], cudaStreamNonBlocking));
+    if (ctx->scratch_busy && ctx->scratch_ev) for (int k = 0; k < 2; k++) CU(cudaStreamWaitEvent(ctx->hs[k], ctx->scratch_ev, 0));
+    // Chunks of whole waves of the N = 2048 blind rotation (4 accumulators per SM, ell1 accumulators per sample) on the two private
+    // streams: the 32 KB-per-sample result of one chunk goes back to the host under the kernels of the next (134 MB per 4096 samples).
+    const int wave = 4 * ctx->sm_count / (ell1 > 0 ? ell1 : 1);
+    const int nchunk = count >= 8 * wave ? 4 : (count >= 2 * wave ? 2 : 1);
+    const int per = wave > 0 ? ((count + nchunk - 1) / nchunk + wave - 1) / wave * wave : count;
+    for (int k = 0, off = 0; off < count; k++, off += per) {
+        const int c = count - off < per ? count - off : per;
+        cudaStream_t s = ctx->hs[k & 1];
+        CU(cudaMemcpyAsync(din + (size_t)off * in_row, sample_host + (size_t)off * in_row, (size_t)c * in_row * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        rc = cb_chunk(ctx, dout + (size_t)off * out_row, din + (size_t)off * in_row, pre + (size_t)off * (n0 + 1), abar + (size_t)off * (n0 + 1),
+                      boot + (size_t)off * ell1 * (N2 + 1), c, s);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(result_host + (size_t)off * out_row, dout + (size_t)off * out_row, (size_t)c * out_row * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(ctx->hs[0]));
+    CU(cudaStreamSynchronize(ctx->hs[1]));
+    ctx->scratch_busy = false;
     return TFHE_B200_OK;
 }
 
@@ -737,14 +989,14 @@ static int hp_tables(tfhe_b200_ctx* ctx, int N, const uint64_t** om, const uint6
     return TFHE_B200_OK;
 }
 int tfhe_b200_hp_iFFT_batch(tfhe_b200_ctx* ctx, tfhe_b200_cplx96* out_dev, const int64_t* in_dev, int N, int count, void* stream) {
-    if (!ctx) return TFHE_B200_ERR_PARAM;
+    ENTER();
     const uint64_t *om, *ob; int rc = hp_tables(ctx, N, &om, &ob); if (rc) return rc;
     NEED(count >= 0, "count < 0"); NEED(count == 0 || (out_dev && in_dev), "null buffer");
     CU(launch_hp_ifft(out_dev, in_dev, om, N, count, (cudaStream_t)stream));
     return TFHE_B200_OK;
 }
 int tfhe_b200_hp_FFT_batch(tfhe_b200_ctx* ctx, int64_t* out_dev, const tfhe_b200_cplx96* in_dev, int N, int count, void* stream) {
-    if (!ctx) return TFHE_B200_ERR_PARAM;
+    ENTER();
     const uint64_t *om, *ob; int rc = hp_tables(ctx, N, &om, &ob); if (rc) return rc;
     NEED(count >= 0, "count < 0"); NEED(count == 0 || (out_dev && in_dev), "null buffer");
     CU(launch_hp_fft(out_dev, in_dev, ob, N, count, (cudaStream_t)stream));

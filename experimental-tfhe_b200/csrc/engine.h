@@ -85,6 +85,9 @@ cudaError_t launch_keyswitch32(const KSArgs& a, cudaStream_t s);
 cudaError_t launch_keyswitch64(const KSArgs& a, cudaStream_t s);
 // raw [rows][t][base][cols] -> device layout
 cudaError_t launch_ks_repack(int32_t* dst, const int32_t* src, int rows, int t, int base, int cols, int cols_pad, cudaStream_t s);
+// the same for a slice [row0, row0 + rows) of rows_total input rows; src holds the slice only
+cudaError_t launch_ks_repack_rows(int32_t* dst, const int32_t* src, int rows_total, int row0, int rows, int t, int base, int cols, int cols_pad,
+                                  cudaStream_t s);
 
 // ------------------------------------------------------------------ small elementwise (misc_kernels.cu)
 cudaError_t launch_lwe_lincomb(int32_t* out, const int32_t* a, const int32_t* b, int ka, int kb, int32_t cconst,

@@ -221,21 +221,29 @@ static cudaError_t launch_ks(KSArgs a, cudaStream_t s) {
 cudaError_t launch_keyswitch32(const KSArgs& a, cudaStream_t s) { return launch_ks<int32_t>(a, s); }
 cudaError_t launch_keyswitch64(const KSArgs& a, cudaStream_t s) { return launch_ks<int64_t>(a, s); }
 
-// raw [rows][t][base][cols] -> [cols_pad/512][rows][t][base-1][512]  (d = 0 dropped, zero padded)
-__global__ void ks_repack_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, size_t nblk, int base, int cols, int cols_pad) {
+// raw [rows][t][base][cols] -> [cols_pad/512][rows][t][base-1][512]  (d = 0 dropped, zero padded).  src holds the blocks
+// [blk0, blk0 + nblk) of nblk_total (a slice of input rows): large keys are staged through a small temporary.
+__global__ void ks_repack_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, size_t nblk_total, size_t blk0, size_t nblk,
+                                 int base, int cols, int cols_pad) {
     const size_t per_group = nblk * (size_t)(base - 1) * 512;
+    const size_t per_group_total = nblk_total * (size_t)(base - 1) * 512;
     const size_t total = per_group * (size_t)(cols_pad / 512);
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const size_t g = e / per_group, r = e % per_group;
         const int c = (int)(g * 512 + r % 512);
         const size_t ro = r / 512;
         const size_t ij = ro / (base - 1); const int d = (int)(ro % (base - 1)) + 1;
-        dst[e] = c < cols ? src[(ij * base + d) * (size_t)cols + c] : 0;
+        dst[g * per_group_total + blk0 * (size_t)(base - 1) * 512 + r] = c < cols ? src[(ij * base + d) * (size_t)cols + c] : 0;
     }
 }
-cudaError_t launch_ks_repack(int32_t* dst, const int32_t* src, int rows, int t, int base, int cols, int cols_pad, cudaStream_t s) {
-    ks_repack_kernel<<<148 * 8, 256, 0, s>>>(dst, src, (size_t)rows * t, base, cols, cols_pad);
+cudaError_t launch_ks_repack_rows(int32_t* dst, const int32_t* src, int rows_total, int row0, int rows, int t, int base, int cols, int cols_pad,
+                                  cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    ks_repack_kernel<<<148 * 8, 256, 0, s>>>(dst, src, (size_t)rows_total * t, (size_t)row0 * t, (size_t)rows * t, base, cols, cols_pad);
     return cudaGetLastError();
+}
+cudaError_t launch_ks_repack(int32_t* dst, const int32_t* src, int rows, int t, int base, int cols, int cols_pad, cudaStream_t s) {
+    return launch_ks_repack_rows(dst, src, rows, 0, rows, t, base, cols, cols_pad, s);
 }
 
 }  // namespace tfhe_b200

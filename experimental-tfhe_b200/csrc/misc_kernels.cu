@@ -4,7 +4,7 @@
 namespace tfhe_b200 {
 
 // boots* linear part [UPSTREAM, SURVEY Appendix C]: out = (0,cconst) + ka*a + kb*b on LWE(n) samples.
-__global__ void lwe_lincomb_kernel(int32_t* __restrict__ out, const int32_t* __restrict__ a, const int32_t* __restrict__ b,
+__global__ void lwe_lincomb_kernel(int32_t* out, const int32_t* a, const int32_t* b,
                                    int ka, int kb, int32_t cconst, int n, size_t total) {
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         uint32_t x = (uint32_t)ka * (uint32_t)a[e];

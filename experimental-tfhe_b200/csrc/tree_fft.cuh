@@ -330,6 +330,60 @@ __device__ __forceinline__ void tree_forward(cplx (&v)[16], cplx* __restrict__ b
     tree_forward_c<LOGM>(v, tw, t);
 }
 
+// Two forward transforms side by side (the two gadget levels cut from one rotated accumulator polynomial): every latency-bound
+// step -- the transposes, the twiddle fetches from tensor memory, the lane exchanges -- is followed by FP64 work of the OTHER data
+// set, so one warp keeps the FP64 pipe fed where a single transform leaves it idle; the twiddles are fetched once for both.
+// One transpose buffer serves both (v goes through first; u's pass A covers v's read-back).
+template <int LOGM, bool TT9 = true>
+__device__ __forceinline__ void tree_forward2(cplx (&v)[16], cplx (&u)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t,
+                                              const int bar_id, const uint32_t ttw) {
+    typedef TreePlan<LOGM> P;
+    constexpr int T = P::T;
+    const int b = t / P::P, p = t % P::P;
+    pass16<false>(v, reinterpret_cast<const cplx*>(c_tree_ta), 1);
+    lanes_sync<T>(bar_id);                                   // WAR: earlier reads of buf
+#pragma unroll
+    for (int m = 0; m < 16; m++) buf[m * P::S + t] = v[m];
+    lanes_sync<T>(bar_id);
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = buf[b * P::S + p + P::P * k];
+    pass16<false>(u, reinterpret_cast<const cplx*>(c_tree_ta), 1);
+    Tw8Regs q; tw8_issue(q, ttw);                            // depths 4-7, shared by both data sets
+    lanes_sync<T>(bar_id);                                   // everybody has read v back
+#pragma unroll
+    for (int m = 0; m < 16; m++) buf[m * P::S + t] = u[m];
+    lanes_sync<T>(bar_id);
+#pragma unroll
+    for (int k = 0; k < 16; k++) u[k] = buf[b * P::S + p + P::P * k];
+    {
+        cplx E[8];
+        tw8_collect(E, q);
+        pass16<false>(v, E, 1);                              // covers u's read-back
+        pass16<false>(u, E, 1);
+    }
+    {   // depth 8
+        Tw8Regs q8; tw8_issue(q8, ttw + 32);
+        odd_swap(v, P::P >> 1); odd_swap(u, P::P >> 1);
+        cplx E[8]; tw8_collect(E, q8);
+#pragma unroll
+        for (int m = 0; m < 8; m++) { bf_fwd(v[2 * m], v[2 * m + 1], E[m]); bf_fwd(u[2 * m], u[2 * m + 1], E[m]); }
+    }
+    if (P::NS > 1) {   // depth 9 (M = 1024)
+        cplx E[8];
+        if constexpr (TT9) {
+            Tw8Regs q9; tw8_issue(q9, ttw + 64);
+            odd_swap(v, 1); odd_swap(u, 1);
+            tw8_collect(E, q9);
+        } else {
+            odd_swap(v, 1); odd_swap(u, 1);
+#pragma unroll
+            for (int m = 0; m < 8; m++) E[m] = tw[P::TC1 + m * T + t];
+        }
+#pragma unroll
+        for (int m = 0; m < 8; m++) { bf_fwd(v[2 * m], v[2 * m + 1], E[m]); bf_fwd(u[2 * m], u[2 * m + 1], E[m]); }
+    }
+}
+
 // Backward: the exact mirror.  in v[i] = spectrum slot i (times g) ; out v[m] = M * z_{t + T m}
 template <int LOGM, bool TT = false>
 __device__ __forceinline__ void tree_backward(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id,

@@ -43,6 +43,27 @@ def replicate_gate_keys(engine, params, bk_host=None, ks_host=None, device=None)
         ptr, nbytes = engine.gate_key_blob(which)
         broadcast_bytes(device_blob_as_tensor(ptr, nbytes, device), src=0)
     torch.cuda.synchronize()
+    if rank != 0:
+        engine.commit_gate_keys()          # only now do the receivers' buffers hold key material
+
+
+def replicate_cb_keys(engine, params, preKS_host=None, bk_host=None, privKS_host=None, device=None, with_privks=True):
+    """Circuit-bootstrap keys, same protocol: rank 0 ingests (device-side transform / repack), the three device blobs -- bk spectra
+    131 MB, preKS 37 MB, privKS 2.35 GB at the reference's parameters -- go to the other ranks by broadcast over NVLink."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if world == 1 or rank == 0:
+        engine.load_cb_keys(params, preKS_host, bk_host, privKS_host if with_privks else None)
+        if world == 1:
+            return
+    else:
+        engine.alloc_cb_keys(params, with_privks)
+    for which in (0, 1, 2) if with_privks else (0, 1):
+        ptr, nbytes = engine.cb_key_blob(which)
+        broadcast_bytes(device_blob_as_tensor(ptr, nbytes, device), src=0)
+    torch.cuda.synchronize()
+    if rank != 0:
+        engine.commit_cb_keys()
 
 
 def max_over_ranks(value, device="cpu"):

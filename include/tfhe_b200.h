@@ -20,6 +20,14 @@
  * (NULL = the legacy default stream).  All *_batch calls on device pointers are asynchronous on
  * `stream`; *_host calls return after the results are in host memory.
  *
+ * Streams and threads.  Calls on one context must come from one host thread at a time (the reference is single-threaded and not
+ * re-entrant either, cb/spqlios/lagrangehalfc_impl.h:14-19), but they may use DIFFERENT streams: the context owns one set of scratch
+ * buffers, and calls that use it (bootstrap_FFT, boots*, bootsMUX, CMux, LUT, CircuitBootstrapFFT, circuit_eval and the *_host
+ * forms) order themselves against each other with an event, so a call queued on stream B starts its kernels after the previous
+ * call's last kernel on stream A -- results are the same as on a single stream.  Calls that do not touch scratch (blindRotate,
+ * bootstrap_woKS, lweKeySwitch, the transforms, hp FFT) run concurrently on their streams.  During CUDA-graph capture the event
+ * ordering is off: replay a captured circuit on one stream at a time.  Every entry point selects the context's device itself.
+ *
  * Errors: the reference has none (assert/abort).  Here every call returns TFHE_B200_OK or a negative
  * code and tfhe_b200_last_error() gives the message.  There is NO CPU fallback: without a usable
  * sm_100 device tfhe_b200_ctx_create fails.
@@ -71,6 +79,9 @@ int tfhe_b200_gate_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p,
  * device blobs are broadcast (NCCL / cudaMemcpyPeer) by the caller.  which: 0 = bk spectra, 1 = ks. */
 int tfhe_b200_gate_alloc_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p);
 int tfhe_b200_gate_key_blob(tfhe_b200_ctx* ctx, int which, void** dev_ptr, size_t* bytes);
+/* The allocated buffers are uninitialised: gates refuse to run (TFHE_B200_ERR_NOKEY) until the caller has filled both blobs and
+ * calls this. */
+int tfhe_b200_gate_commit_keys(tfhe_b200_ctx* ctx);
 /* Wire format of the LOADED gate keys (the reference has no serialization and rebuilds its keys on every run,
  * cb/poc_CircuitBootstrapping.cpp:342-423): a 96-byte header -- magic "TFHEB200", format version, the seven parameters, the two
  * blob sizes, an FNV-1a checksum of the payload -- followed by the bootstrapping-key spectra and the repacked key-switching key
@@ -188,6 +199,23 @@ typedef struct {
  * bk[n0][2*l2][2][N2] (Torus64, coefficient domain), privKS[2][N2+1][t21][base21][2][N1] or NULL. */
 int tfhe_b200_cb_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p, const int32_t* preKS_host,
                            const int64_t* bk_host, const int32_t* privKS_host);
+/* Multi-GPU replication of the circuit-bootstrap keys, same protocol as the gate keys: rank 0 loads, every other rank
+ * allocates, the device blobs are broadcast by the caller (which: 0 = bk spectra, 1 = preKS, 2 = privKS), then commit. */
+int tfhe_b200_cb_alloc_keys(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p, int with_privks);
+int tfhe_b200_cb_key_blob(tfhe_b200_ctx* ctx, int which, void** dev_ptr, size_t* bytes);
+int tfhe_b200_cb_commit_keys(tfhe_b200_ctx* ctx);
+/* Wire format of the LOADED circuit-bootstrap keys (the reference rebuilds them on every run, ~100 s,
+ * cb/poc_CircuitBootstrapping.cpp:342-423): a 128-byte header (magic "TFHEB200", format version, kind 2, the eleven parameters,
+ * the three blob sizes, FNV-1a checksum) followed by the three device blobs.  Both directions move the 2.35 GB private key-switch
+ * key without a full-size temporary.  export: buf_host = NULL returns the size in *bytes. */
+int tfhe_b200_cb_export_keys(tfhe_b200_ctx* ctx, void* buf_host, size_t* bytes);
+int tfhe_b200_cb_import_keys(tfhe_b200_ctx* ctx, const void* buf_host, size_t bytes);
+/* Ciphertext wire format (the reference has none): 64-byte header (magic "TFHEB2CT", version, kind: 1 LWE32,
+ * 2 LWE64, 3 TLWE32, 4 TGSW32; up to four dimensions, slowest first, unused = 0; payload size; FNV-1a checksum) followed by the
+ * samples in the flat layouts listed at the top of this header.  Host-side only, no context needed (errors: tfhe_b200_last_error(NULL)).
+ * pack: buf_host = NULL returns the size.  unpack: samples_host = NULL returns kind, dims and the payload size. */
+int tfhe_b200_ciphertext_pack(int kind, const int64_t dims[4], const void* samples_host, void* buf_host, size_t* bytes);
+int tfhe_b200_ciphertext_unpack(const void* buf_host, size_t bytes, int* kind, int64_t dims[4], void* samples_host, size_t* sample_bytes);
 /* preKeySwitch (:437-465): result[B][n0+1], x[B][N1+1] */
 int tfhe_b200_preKeySwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* x_dev, int count, void* stream);
 /* preModSwitch (:472-484): result[B][n0+1] in [0, 2*N2) */

@@ -14,6 +14,7 @@ template <int MODE> __global__ void __launch_bounds__(256) k(double* out, const 
     double a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
     int x0 = in[t], x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
     double2 s = make_double2(0, 0);
+    double c0 = t, c1 = t + 1, c2 = t + 2, c3 = t + 3, c4 = t + 4, c5 = t + 5, c6 = t + 6, c7 = t + 7;      // MODE 13
     for (int it = 0; it < iters; it++) {
         if (MODE == 0) {            // DFMA only
             a0 = fma(a0, 1.0000001, 1e-9); a1 = fma(a1, 1.0000001, 1e-9); a2 = fma(a2, 1.0000001, 1e-9); a3 = fma(a3, 1.0000001, 1e-9);
@@ -64,6 +65,33 @@ template <int MODE> __global__ void __launch_bounds__(256) k(double* out, const 
 #pragma unroll
             for (int u = 0; u < 8; u++) { double2 v = sm[(t * 8 + u + (t >> 2)) & 2047]; s.x += v.x; s.y += v.y; }
             a0 += s.x;
+        } else if (MODE == 11) {    // DMMA m8n8k4 (256 FMA per warp instruction), 4 independent accumulators
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%4}, {%5}, {%0,%1};\n\t"
+                         "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%4}, {%5}, {%2,%3};"
+                         : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3) : "d"(a6), "d"(a7));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%4}, {%5}, {%0,%1};\n\t"
+                         "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%4}, {%5}, {%2,%3};"
+                         : "+d"(a4), "+d"(a5), "+d"(s.x), "+d"(s.y) : "d"(a6), "d"(a7));
+        } else if (MODE == 12) {    // DMMA m16n8k16 (2048 FMA per warp instruction), 2 independent accumulators
+            double b0 = a6, b1 = a7, b2 = a6 + 1, b3 = a7 + 1;
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, {%0,%1,%2,%3};"
+                         : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3)
+                         : "d"(b0), "d"(b1), "d"(b2), "d"(b3), "d"(b0), "d"(b1), "d"(b2), "d"(b3), "d"(b0), "d"(b1), "d"(b2), "d"(b3));
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, {%0,%1,%2,%3};"
+                         : "+d"(a4), "+d"(a5), "+d"(s.x), "+d"(s.y)
+                         : "d"(b0), "d"(b1), "d"(b2), "d"(b3), "d"(b0), "d"(b1), "d"(b2), "d"(b3), "d"(b0), "d"(b1), "d"(b2), "d"(b3));
+        } else if (MODE == 13) {    // 4 DMMA m8n8k4 + 32 DFMA per iteration: do the tensor and the vector FP64 paths add up?
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%4}, {%5}, {%0,%1};\n\t"
+                         "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%4}, {%5}, {%2,%3};"
+                         : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3) : "d"(a6), "d"(a7));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%4}, {%5}, {%0,%1};\n\t"
+                         "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%4}, {%5}, {%2,%3};"
+                         : "+d"(a4), "+d"(a5), "+d"(s.x), "+d"(s.y) : "d"(a6), "d"(a7));
+#pragma unroll
+            for (int u = 0; u < 4; u++) {      // loop-carried (c0..c7 live across iterations), so the 32 DFMA stay in the loop
+                c0 = fma(c0, 1.0000001, 1e-9); c1 = fma(c1, 1.0000001, 1e-9); c2 = fma(c2, 1.0000001, 1e-9); c3 = fma(c3, 1.0000001, 1e-9);
+                c4 = fma(c4, 1.0000001, 1e-9); c5 = fma(c5, 1.0000001, 1e-9); c6 = fma(c6, 1.0000001, 1e-9); c7 = fma(c7, 1.0000001, 1e-9);
+            }
         } else if (MODE == 10) {    // integer bit-trick double->int64 trunc (8 per iter), integer pipe only
 #pragma unroll
             for (int u = 0; u < 8; u++) {
@@ -75,7 +103,7 @@ template <int MODE> __global__ void __launch_bounds__(256) k(double* out, const 
             }
         }
     }
-    out[blockIdx.x * 256 + t] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + s.x + s.y + x0 + x1 + x2 + x3;
+    out[blockIdx.x * 256 + t] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + s.x + s.y + x0 + x1 + x2 + x3 + (MODE == 13 ? c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7 : 0.0);
 }
 
 template <int MODE> void run(const char* name, double ops_per_iter_per_thread, const char* unit) {
@@ -105,5 +133,10 @@ int main() {
     run<8>("8 SHFL + 8 LDS.128", 8 * 4 + 8 * 16, "B");
     run<9>("8 STS.128 + 8 LDS.128", 16 * 16, "B");
     run<10>("int bit-trick f64->i64 trunc", 8, "cvt");
+    // FP64 tensor path (north star: tensor cores only if a DFT-as-GEMM beats the butterflies).  fma counts per THREAD per iteration:
+    // one m8n8k4 = 256 FMA per warp = 8 per thread; one m16n8k16 = 2048 per warp = 64 per thread.
+    run<11>("DMMA m8n8k4 x4", 4 * 8, "fma");
+    run<12>("DMMA m16n8k16 x2", 2 * 64, "fma");
+    run<13>("4 DMMA m8n8k4 + 32 DFMA (both counted)", 4 * 8 + 32, "fma");
     return 0;
 }
