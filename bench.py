@@ -68,6 +68,238 @@ def cpu_gate_rate(count, threads):
     return count / dt, "port", f"{count} bootsNAND on {threads} threads: oracle port with its portable FFT"
 
 
+def _harness(args, timeout=900):
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(harness):
+        return None
+    try:
+        r = subprocess.run([harness] + [str(a) for a in args], capture_output=True, text=True, timeout=timeout)
+        return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    except Exception:
+        return None
+
+
+def cpu_cb_rate(count, threads):
+    """Reference CPU circuit bootstrap: the oracle's tfhe_CircuitBootstrapFFT (bit-identical to the reference's, tests/golden/pin_log.txt)
+    over the reference's spqlios kernels, OpenMP over samples (oracle/_ref); else the portable port on one thread."""
+    d = _harness(["bench-cb", count, threads])
+    if d:
+        return d["cb_per_s"], "reference", f"{count} tfhe_CircuitBootstrapFFT on {threads} threads: oracle path over the reference's spqlios-fma FFT (oracle/_ref)", threads
+    import numpy as np
+    import oracle_lib as O
+    c = O.CBOracle(42)
+    x = np.random.default_rng(45).integers(-2**31, 2**31 - 1, size=(2, c.N1 + 1), dtype=np.int64).astype(np.int32)
+    t0 = time.perf_counter(); c.CircuitBootstrapFFT(x); dt = time.perf_counter() - t0
+    return 2 / dt, "port", "2 tfhe_CircuitBootstrapFFT on 1 thread: oracle port with its portable FFT", 1
+
+
+def cpu_hp_rate(N, count, threads):
+    d = _harness(["bench-hp", N, count, threads])
+    if d:
+        return d["ifft_per_s"], d["fft_per_s"], "port", f"{count} transforms each way on {threads} threads: hp/code.cpp restated (oracle/hpfft_oracle.c, -Ofast)", threads
+    import numpy as np
+    import oracle_lib as O
+    om, ob = O.hp_tables(N)
+    x = np.random.default_rng(46).integers(-2**63, 2**63 - 1, size=(8, N), dtype=np.int64)
+    t0 = time.perf_counter(); sp = [O.hp_iFFT(x[i], N, om) for i in range(8)]; t1 = time.perf_counter()
+    [O.hp_FFT(sp[i], N, ob) for i in range(8)]; t2 = time.perf_counter()
+    return 8 / (t1 - t0), 8 / (t2 - t1), "port", "8 transforms each way on 1 thread: hp/code.cpp restated (oracle/hpfft_oracle.c)", 1
+
+
+CB_PARAMS = dict(n_lvl0=500, N_lvl1=1024, N_lvl2=2048, bgbit_lvl1=8, ell_lvl1=2, bgbit_lvl2=9, ell_lvl2=4,
+                 kslength_lvl10=6, ksbasebit_lvl10=2, kslength_lvl21=10, ksbasebit_lvl21=3)      # cb/poc_CircuitBootstrapping.cpp:70-85
+FLOP_PER_CB = 704.512e6          # SURVEY 8d: 2 blind rotations x 500 CMUX x 704,512 flop
+CB_BATCH = 4096
+
+
+def _traffic(kernel):
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", name)))[kernel]
+            return tr
+        except Exception:
+            continue
+    return None
+
+
+def section_circuit_bootstrap(torch, np, eng, par, dist, rank, world, dev, fp64_peak, steps, cpu_baseline):
+    """BASELINE configs[3]: 4,096 independent tfhe_CircuitBootstrapFFT per GPU at the reference's active parameter set
+    (cb/poc_CircuitBootstrapping.cpp:70-85, timing loop :1008-1016), keys of those shapes (uniform random), weak scaling."""
+    p = CB_PARAMS
+    B = CB_BATCH
+    pre = bk = priv = None
+    t0 = time.perf_counter()
+    if rank == 0:
+        krng = np.random.default_rng(43)
+        bk = krng.integers(-2**63, 2**63 - 1, size=(p["n_lvl0"], 2 * p["ell_lvl2"], 2, p["N_lvl2"]), dtype=np.int64)
+        pre = krng.integers(-2**31, 2**31 - 1, size=(p["N_lvl1"], p["kslength_lvl10"], 1 << p["ksbasebit_lvl10"], p["n_lvl0"] + 1), dtype=np.int32)
+        priv = krng.integers(-2**31, 2**31 - 1, size=(2, p["N_lvl2"] + 1, p["kslength_lvl21"], 1 << p["ksbasebit_lvl21"], 2, p["N_lvl1"]), dtype=np.int32)
+    t_gen = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    par.replicate_cb_keys(eng, p, pre, bk, priv, device=dev)
+    torch.cuda.synchronize()
+    t_rep = par.max_over_ranks(time.perf_counter() - t0, device=dev)
+    del pre, bk, priv
+    gen = torch.Generator(device=dev).manual_seed(45 + rank)
+    x = torch.randint(-2**31, 2**31 - 1, (B, p["N_lvl1"] + 1), dtype=torch.int64, device=dev, generator=gen).to(torch.int32)
+    res = torch.empty((B, 2, p["ell_lvl1"], 2, p["N_lvl1"]), dtype=torch.int32, device=dev)
+    h_x = torch.empty(x.shape, dtype=torch.int32).pin_memory(); h_x.copy_(x)
+    h_res = torch.empty(res.shape, dtype=torch.int32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.tfhe_CircuitBootstrapFFT(res, x, B)
+    barrier()
+    eng.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.tfhe_CircuitBootstrapFFT(res, x, B)
+    e1.record()
+    barrier()
+    ms = par.max_over_ranks(e0.elapsed_time(e1), device=dev) / steps
+    kern_ms, kern_n = eng.profile_read()
+    eng.profile_enable(False)
+    eng.tfhe_CircuitBootstrapFFT_host(h_res, h_x, B)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.tfhe_CircuitBootstrapFFT_host(h_res, h_x, B)
+    torch.cuda.synchronize()
+    t_e2e = par.max_over_ranks(time.perf_counter() - t0, device=dev) / steps
+    checksum = int(h_res[:, 1, 0, 1, 0].to(torch.int64).sum().item())
+    barrier()
+    if rank != 0:
+        return None
+    br_ms = kern_ms["blind_rotate"] / max(kern_n["blind_rotate"], 1)
+    ks_ms = kern_ms["keyswitch"] / steps                       # preKS + the one launch of all four private key switches
+    tf = FLOP_PER_CB * B / (br_ms * 1e-3) / 1e12
+    tr_br, tr_ks = _traffic("blind_rotate_kernel_n2048"), _traffic("keyswitch_kernel_privks")
+    out = {"metric": "circuit bootstraps/sec (batch 4096)", "value": world * B / (ms * 1e-3), "unit": "circuit bootstraps/s", "ms_per_step": ms,
+           "steps": steps, "scaling": "weak",
+           "config": {"workload": "4096 tfhe_CircuitBootstrapFFT per GPU, n0=500 N1=1024 N2=2048 l1=2 Bg1=2^8 l2=4 Bg2=2^9, KS10 6x2 bit, KS21 10x3 bit",
+                      "batch_per_gpu": B},
+           "e2e": {"value": world * B / t_e2e, "unit": "circuit bootstraps/s", "h2d_bytes_per_step": int(h_x.numel()) * 4,
+                   "d2h_bytes_per_step": int(h_res.numel()) * 4, "api": "tfhe_b200_CircuitBootstrapFFT_batch_host", "result_checksum": checksum},
+           "kernel_ms_per_step": {"blind_rotate": br_ms, "keyswitch": ks_ms, "other": kern_ms["other"] / steps},
+           "roofline": {"bound": "fp64", "kernel": "blind_rotate_kernel<10,int64_t>", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                        "frac": tf / fp64_peak if fp64_peak else None,
+                        "traffic": tr_br["dram_bytes_per_launch"] if tr_br and tr_br.get("batch") == B else None,
+                        "traffic_source": tr_br["source"] if tr_br and tr_br.get("batch") == B else None,
+                        "algorithmic": "704.5 MFLOP per circuit bootstrap (both mu_w in one launch: 8192 rotations of 352.3 MFLOP)"},
+           "privks": {"kernel": "keyswitch_kernel<int64_t,3> (4 private key switches, one launch)", "ms": ks_ms,
+                      "table_bytes": 2 * (p["N_lvl2"] + 1) * p["kslength_lvl21"] * 7 * 2 * p["N_lvl1"] * 4,
+                      "int32_adds_per_cb": 146.9e6,
+                      "traffic": tr_ks["dram_bytes_per_launch"] if tr_ks and tr_ks.get("batch") == B else None,
+                      "traffic_source": tr_ks["source"] if tr_ks and tr_ks.get("batch") == B else None},
+           "key_replication_ms": t_rep * 1e3, "key_bytes_replicated": 131072000 + 37748736 + 2349858816, "host_keygen_s": t_gen,
+           "gpu_launches": int(sum(kern_n.values()))}
+    if cpu_baseline and world == 1:
+        threads = host_threads()
+        rate, kind, sample, used = cpu_cb_rate(max(2 * threads, 8), threads)
+        out["cpu_baseline"] = {"value": rate, "unit": "circuit bootstraps/s", "cores": used, "kind": kind, "sample": sample}
+    return out
+
+
+def section_hp_fft(torch, np, eng, par, dist, rank, world, dev, cpu_baseline):
+    """BASELINE configs[4] (standalone): 128-bit fixed-point anticyclic FFT, N = 2048 / 4096, 16,384 polynomials per GPU
+    (hp/code.cpp:391-512; the reference times it at :574-586)."""
+    B = 16384
+    peak = eng.probe_real96_gprods() if rank == 0 else 0.0
+    res = {}
+    for N, cprod in ((2048, 6144), (4096, 13312)):              # complex fixed-point products per transform (SURVEY 8d)
+        gen = torch.Generator(device=dev).manual_seed(46 + rank)
+        x = torch.randint(-2**63, 2**63 - 1, (B, N), dtype=torch.int64, device=dev, generator=gen)
+        spec = torch.empty((B, N // 2, 4), dtype=torch.int64, device=dev)
+        back = torch.empty((B, N), dtype=torch.int64, device=dev)
+        eng.hp_iFFT(spec, x, N, B); eng.hp_FFT(back, spec, N, B)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        reps = 5
+        ev[0].record()
+        for _ in range(reps):
+            eng.hp_iFFT(spec, x, N, B)
+        ev[1].record()
+        for _ in range(reps):
+            eng.hp_FFT(back, spec, N, B)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t_i = par.max_over_ranks(ev[0].elapsed_time(ev[1]), device=dev) / reps
+        t_f = par.max_over_ranks(ev[1].elapsed_time(ev[2]), device=dev) / reps
+        err = int((back - x).abs().max().item())
+        if rank == 0:
+            ach_i = 4 * cprod * B / (t_i * 1e-3) / 1e9
+            ach_f = 4 * cprod * B / (t_f * 1e-3) / 1e9
+            res[f"N{N}"] = {"batch_per_gpu": B, "iFFT_per_s": world * B / (t_i * 1e-3), "FFT_per_s": world * B / (t_f * 1e-3), "iFFT_ms": t_i, "FFT_ms": t_f,
+                            "roundtrip_max_err_lsb": err,
+                            "roofline": {"bound": "int64-multiply", "kernel": "hp_ifft_kernel / hp_fft_kernel", "unit": "G real96 products/s",
+                                         "achieved": ach_i, "achieved_fft": ach_f, "peak": peak, "frac": ach_i / peak if peak else None,
+                                         "frac_fft": ach_f / peak if peak else None,
+                                         "algorithmic": f"{cprod} complex products x 4 real96 products per transform (SURVEY 8d)",
+                                         "peak_source": "real96_mul probe (same arithmetic, operands in registers) measured in this run",
+                                         "hbm_bytes_per_transform": N * 8 + N // 2 * 32}}
+            if cpu_baseline and world == 1:
+                threads = host_threads()
+                ri, rf, kind, sample, used = cpu_hp_rate(N, 64 * threads, threads)
+                res[f"N{N}"]["cpu_baseline"] = {"value": ri, "value_fft": rf, "unit": "transforms/s", "cores": used, "kind": kind, "sample": sample}
+        del x, spec, back
+    if rank != 0:
+        return None
+    return {"metric": "128-bit fixed-point anticyclic FFT transforms/sec (batch 16384)", "unit": "transforms/s", "scaling": "weak",
+            "value": res["N2048"]["iFFT_per_s"], **res}
+
+
+def adder_netlist(mod, bits):
+    """32-bit ripple-carry adder, 5 bootstrapped gates per bit: wires a[bits] b[bits] cin | x[bits] | s[bits] | carries"""
+    G = mod.GATES
+    a0, b0, cin = 0, bits, 2 * bits
+    x0 = cin + 1; s0 = x0 + bits; c0 = s0 + bits; t0 = c0 + bits; u0 = t0 + bits
+    gates = [(G["XOR"], x0 + i, a0 + i, b0 + i, 0) for i in range(bits)]            # one merged launch of `bits` gates
+    gates += [(G["AND"], t0 + i, a0 + i, b0 + i, 0) for i in range(bits)]           # and another
+    for i in range(bits):
+        c_in = cin if i == 0 else c0 + i - 1
+        gates.append((G["XOR"], s0 + i, x0 + i, c_in, 0))
+        gates.append((G["AND"], u0 + i, x0 + i, c_in, 0))
+        gates.append((G["OR"], c0 + i, t0 + i, u0 + i, 0))
+    return gates, dict(a0=a0, b0=b0, cin=cin, s0=s0, n_wires=u0 + bits)
+
+
+def section_adder32(torch, np, mod, eng, par, dist, rank, world, dev, total_adders):
+    """BASELINE configs[2]: 32-bit ripple-carry adders, the batch sharded over the GPUs (strong scaling: `total_adders` in total),
+    gate keys replicated.  Inputs are synthetic ciphertexts: timing is data independent; sums are checked in tests/test_gpu_circuit.py."""
+    lo, hi = par.shard_range(total_adders, rank, world)
+    B = hi - lo
+    bits = 32
+    gates, w = adder_netlist(mod, bits)
+    n = eng.gate_params.n
+    gen = torch.Generator(device=dev).manual_seed(47 + rank)
+    wires = torch.randint(-2**31, 2**31 - 1, (w["n_wires"], max(B, 1), n + 1), dtype=torch.int64, device=dev, generator=gen).to(torch.int32)
+    if B > 0:
+        eng.circuit_eval(gates, wires, w["n_wires"], B)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    if B > 0:
+        eng.circuit_eval(gates, wires, w["n_wires"], B)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = par.max_over_ranks(e0.elapsed_time(e1), device=dev)
+    if rank != 0:
+        return None
+    return {"metric": "32-bit ripple-carry adders/sec", "value": total_adders / (ms * 1e-3), "unit": "adders/s", "ms": ms, "scaling": "strong",
+            "bootstrapped_gates_per_s": 160 * total_adders / (ms * 1e-3),
+            "config": {"workload": f"{total_adders} adders in total, sharded {world} ways (contiguous ranges), 160 bootstrapped gates each, "
+                                   "carry chain = 64 dependent levels of `adders per GPU` gates", "adders_per_gpu": B}}
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -169,6 +401,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="gates per GPU per step (default: the BASELINE configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gate-only", action="store_true", help="skip the circuit-bootstrap / hp-FFT / adder sections")
+    ap.add_argument("--adders", type=int, default=2048, help="32-bit adders in total (sharded over the GPUs)")
     args = ap.parse_args()
     _guard_stdout()
     if args.impl == "reference":
@@ -202,7 +436,11 @@ def main():
         bk_host = krng.integers(-2**31, 2**31 - 1, size=(params["n"], 2 * params["bk_l"], 2, params["N"]), dtype=np.int64).astype(np.int32)
         ks_host = krng.integers(-2**31, 2**31 - 1, size=(params["N"], params["ks_t"], 1 << params["ks_basebit"], params["n"] + 1),
                                 dtype=np.int64).astype(np.int32)
+    torch.cuda.synchronize()
+    t_rep0 = time.perf_counter()
     par.replicate_gate_keys(eng, params, bk_host, ks_host, device=dev)
+    torch.cuda.synchronize()
+    gate_key_ms = par.max_over_ranks(time.perf_counter() - t_rep0, device=dev) * 1e3      # ingest on rank 0 + broadcast, once per job
     n = params["n"]
 
     # synthetic ciphertexts: i.i.d. uniform int32 (timing is data independent), distinct per rank
@@ -258,6 +496,27 @@ def main():
     checksum = int(h_out[:, n].to(torch.int64).sum().item())      # the device->host result is really read
     barrier()
 
+    # ---- strong scaling of the same metric: 65,536 gates IN TOTAL, sharded over the ranks (tail waves and launch overhead show here)
+    lo, hi = par.shard_range(B, rank, world)
+    sB = hi - lo
+    eng.bootsGate("NAND", out, ca, cb, sB)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        eng.bootsGate("NAND", out, ca, cb, sB)
+    s1.record()
+    barrier()
+    strong_ms = par.max_over_ranks(s0.elapsed_time(s1), device=dev) / args.steps
+
+    extra = {}
+    if not args.gate_only:
+        del h_ca, h_cb, h_out
+        extra["adder32"] = section_adder32(torch, np, mod, eng, par, dist, rank, world, dev, args.adders)
+        extra["hp_fft"] = section_hp_fft(torch, np, eng, par, dist, rank, world, dev, not args.no_cpu_baseline)
+        extra["circuit_bootstrap"] = section_circuit_bootstrap(torch, np, eng, par, dist, rank, world, dev, fp64_peak,
+                                                               min(args.steps, 3), not args.no_cpu_baseline)
+
     if rank == 0:
         gates = world * B * args.steps
         value = gates / (ms_total * 1e-3)
@@ -301,7 +560,11 @@ def main():
                              "unit": "GB/s", "peak_source": hbm_src,
                              "note": "ciphertext I/O only (6012 B per gate); the 32.8 MB key stream is L2 resident"},
             "clocks": clocks,
+            "strong": {"scaling": "strong", "value": B / (strong_ms * 1e-3), "unit": "gates/s", "ms_per_step": strong_ms,
+                       "config": {"workload": f"{B} bootsNAND in total, sharded {world} ways", "gates_per_gpu": sB}},
+            "key_replication_ms": gate_key_ms, "key_bytes_replicated": 32768000 + 50331648,
         }
+        line.update({k: v for k, v in extra.items() if v is not None})
         if not args.no_cpu_baseline and world == 1:
             threads = host_threads()
             rate, kind, sample = cpu_gate_rate(threads * 256, threads)

@@ -102,6 +102,8 @@ _SIGS = {
     "tfhe_b200_profile_enable": [_P, _I],
     "tfhe_b200_profile_read": [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)],
     "tfhe_b200_probe_fp64_tflops": [_P, ctypes.POINTER(ctypes.c_double)],
+    "tfhe_b200_blindRotate64_FFT_batch": [_P, _P, _P, _I, _P],
+    "tfhe_b200_probe_real96_gprods": [_P, ctypes.POINTER(ctypes.c_double)],
     "tfhe_b200_probe_read_gbs": [_P, ctypes.c_size_t, _I, ctypes.POINTER(ctypes.c_double)],
 }
 EXPORTS = sorted(list(_SIGS) + ["tfhe_b200_last_error"])
@@ -234,6 +236,11 @@ class Engine:
         self._ck(self.lib.tfhe_b200_probe_fp64_tflops(self.h, ctypes.byref(v)), "probe_fp64_tflops")
         return v.value
 
+    def probe_real96_gprods(self):
+        v = ctypes.c_double()
+        self._ck(self.lib.tfhe_b200_probe_real96_gprods(self.h, ctypes.byref(v)), "probe_real96_gprods")
+        return v.value
+
     def probe_read_gbs(self, nbytes, passes):
         v = ctypes.c_double()
         self._ck(self.lib.tfhe_b200_probe_read_gbs(self.h, nbytes, passes, ctypes.byref(v)), "probe_read_gbs")
@@ -358,6 +365,9 @@ class Engine:
         p = CBParams(**params) if isinstance(params, dict) else params
         self._ck(self.lib.tfhe_b200_cb_load_keys(self.h, ctypes.byref(p), _ptr(preKS_host), _ptr(bk_host), _ptr(privKS_host)), "cb_load_keys")
         self.cb_params = p
+
+    def blindRotate64_FFT(self, accum, bara, count, stream=None):
+        self._ck(self.lib.tfhe_b200_blindRotate64_FFT_batch(self.h, _ptr(accum), _ptr(bara), count, self._stream(stream)), "blindRotate64_FFT")
 
     def alloc_cb_keys(self, params, with_privks=True):
         p = CBParams(**params) if isinstance(params, dict) else params

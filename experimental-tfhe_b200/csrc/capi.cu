@@ -882,6 +882,17 @@ static int cb_woks(tfhe_b200_ctx* ctx, int64_t* result_dev, int64_t mu, int n_mu
     { ProfScope ps(ctx, 0, s); CU(launch_blind_rotate64(a, s)); }
     return TFHE_B200_OK;
 }
+// the blind-rotation loop alone on Torus64 accumulators (cb/poc_CircuitBootstrapping.cpp:580-642 with defects D1/D2 corrected):
+// accum[B][2][N2] in/out, bara[B][n0] rotation amounts in [0, 2*N2)
+int tfhe_b200_blindRotate64_FFT_batch(tfhe_b200_ctx* ctx, int64_t* accum_dev, const int32_t* bara_dev, int count, void* stream) {
+    NEED_CB(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (accum_dev && bara_dev), "null buffer");
+    const tfhe_b200_cb_params& p = ctx->cp;
+    BRArgs a{};
+    a.bkfft = ctx->c_bkfft; a.tw = ctx->tw2048; a.n = p.n_lvl0; a.l = p.ell_lvl2; a.Bgbit = p.bgbit_lvl2; a.count = count;
+    a.mode = BR_ACCUM; a.accum = accum_dev; a.bara = bara_dev; a.n_mu = 1; a.out_stride = p.N_lvl2 + 1;
+    { ProfScope ps(ctx, 0, (cudaStream_t)stream); CU(launch_blind_rotate64(a, (cudaStream_t)stream)); }
+    return TFHE_B200_OK;
+}
 int tfhe_b200_circuitBootstrapWoKS_batch(tfhe_b200_ctx* ctx, int64_t* result_dev, int64_t mu, const int32_t* abar_dev, int count, void* stream) {
     NEED_CB(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (result_dev && abar_dev), "null buffer");
     return cb_woks(ctx, result_dev, mu, 1, 0, abar_dev, count, (cudaStream_t)stream);
@@ -1027,6 +1038,13 @@ int tfhe_b200_probe_fp64_tflops(tfhe_b200_ctx* ctx, double* tflops) {
     NEED(tflops, "probe: null output");
     CU(cudaSetDevice(ctx->device));
     CU(probe_fp64(tflops));
+    return TFHE_B200_OK;
+}
+int tfhe_b200_probe_real96_gprods(tfhe_b200_ctx* ctx, double* gprods) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(gprods, "probe: null output");
+    CU(cudaSetDevice(ctx->device));
+    CU(probe_real96(gprods));
     return TFHE_B200_OK;
 }
 int tfhe_b200_probe_read_gbs(tfhe_b200_ctx* ctx, size_t bytes, int passes, double* gbs) {

@@ -104,5 +104,6 @@ cudaError_t launch_modswitch(int32_t* out, const int32_t* in, int Msize_log2, si
 cudaError_t launch_hp_ifft(tfhe_b200_cplx96* out, const int64_t* in, const uint64_t* powomega, int N, int count, cudaStream_t s);
 cudaError_t launch_hp_fft(int64_t* out, const tfhe_b200_cplx96* in, const uint64_t* powombar, int N, int count, cudaStream_t s);
 cudaError_t hp_init();
+cudaError_t probe_real96(double* gprod_per_s);   // sustained rate of real96 products (10^9 / s): the hp FFT's arithmetic roofline
 
 }  // namespace tfhe_b200

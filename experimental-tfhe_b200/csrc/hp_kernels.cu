@@ -171,4 +171,39 @@ cudaError_t launch_hp_fft(int64_t* out, const tfhe_b200_cplx96* in, const uint64
     return cudaGetLastError();
 }
 
+// Arithmetic roofline of the 128-bit transforms: the rate of real96 products (the same real96_mul, eight independent chains per
+// thread, operands in registers) that this GPU sustains -- measured in the bench run, next to the transforms it bounds.
+__global__ void __launch_bounds__(256) real96_probe_kernel(uint64_t* out, int iters, uint64_t seed) {
+    u128 a[8], b[2];
+    for (int i = 0; i < 8; i++) a[i] = ((u128)(seed + threadIdx.x + i) << 64) | (0x9E3779B97F4A7C15ull * (threadIdx.x + i + 1));
+    b[0] = (u128)(0xB5297A4D3F84D5B5ull ^ seed);                       // twiddles in [0,1): high word 0
+    b[1] = ~(u128)0 << 64 | (0x68E31DA4B5297A4Dull + seed);            // and in [-1,0): high word -1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = real96_mul(a[i], b[i & 1]) + (u128)it;
+    }
+    uint64_t s = 0;
+    for (int i = 0; i < 8; i++) s ^= (uint64_t)a[i] ^ (uint64_t)(a[i] >> 64);
+    if (s == 0x1234567) out[0] = s;
+}
+cudaError_t probe_real96(double* gprod_per_s) {
+    uint64_t* d; cudaError_t e = cudaMalloc(&d, 8); if (e != cudaSuccess) return e;
+    const int grid = 148 * 8, iters = 1 << 13;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    real96_probe_kernel<<<grid, 256>>>(d, 256, 1);
+    double best = 0;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0);
+        real96_probe_kernel<<<grid, 256>>>(d, iters, 7 + rep);
+        cudaEventRecord(e1); e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) break;
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        const double g = 8.0 * (double)iters * 256 * grid / (ms * 1e-3) / 1e9;
+        if (g > best) best = g;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *gprod_per_s = best;
+    return e;
+}
+
 }  // namespace tfhe_b200

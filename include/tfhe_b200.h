@@ -220,6 +220,9 @@ int tfhe_b200_ciphertext_unpack(const void* buf_host, size_t bytes, int* kind, i
 int tfhe_b200_preKeySwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* x_dev, int count, void* stream);
 /* preModSwitch (:472-484): result[B][n0+1] in [0, 2*N2) */
 int tfhe_b200_preModSwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* x_dev, int count, void* stream);
+/* The blind-rotation loop of circuitBootstrapWoKS alone (:580-642, defects D1/D2 of SURVEY Appendix B corrected) on Torus64
+ * accumulators: accum[B][2][N2] in/out, bara[B][n0] in [0, 2*N2).  The Torus64 twin of tfhe_b200_blindRotate_FFT_batch. */
+int tfhe_b200_blindRotate64_FFT_batch(tfhe_b200_ctx* ctx, int64_t* accum_dev, const int32_t* bara_dev, int count, void* stream);
 /* circuitBootstrapWoKS (:530-659, with the corrections D1-D3 of SURVEY Appendix B):
  * result[B][N2+1] (Torus64), abar[B][n0+1]. */
 int tfhe_b200_circuitBootstrapWoKS_batch(tfhe_b200_ctx* ctx, int64_t* result_dev, int64_t mu,
@@ -258,6 +261,9 @@ int tfhe_b200_profile_read(tfhe_b200_ctx* ctx, double ms[3], int launches[3]);
 /* Measured FP64 FMA throughput of this GPU (dependent-chain-free DFMA kernel), in TFLOP/s (2 flop per FMA). */
 int tfhe_b200_probe_fp64_tflops(tfhe_b200_ctx* ctx, double* tflops);
 /* Measured read bandwidth over a `bytes`-sized buffer that is re-read `passes` times (L2-resident when small), GB/s. */
+/* sustained rate (10^9 per second) of 128-bit fixed-point products (hp/code.cpp:148-169 intmul_best) with operands in registers:
+ * the arithmetic roofline of the high-precision FFT, measured next to it */
+int tfhe_b200_probe_real96_gprods(tfhe_b200_ctx* ctx, double* gprods);
 int tfhe_b200_probe_read_gbs(tfhe_b200_ctx* ctx, size_t bytes, int passes, double* gbs);
 
 #ifdef __cplusplus

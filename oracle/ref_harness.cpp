@@ -281,10 +281,61 @@ static int cmd_bench_cb(int count) {
     return 0;
 }
 
+// circuit bootstraps on `threads` cores: the oracle's tfhe_CircuitBootstrapFFT (pinned bit for bit against the reference's own,
+// cmd_golden) over the reference's spqlios kernels, OpenMP over independent samples -- the reference's only threading idiom
+// (par/test_parallel_multiplications.cpp:62); its own entry point keeps shared scratch in Globals and cannot run on two threads.
+static int cmd_bench_cb_mt(int count, int threads) {
+    orc_set_fft_backend(&kSpqlios);
+    orc_cb_params cp; orc_cb_params_default(&cp);
+    orc_cb_keys* K = orc_cb_keygen(&cp, 42, 1);
+    orc_cb_keys_rebuild_fft(K);
+    const int N1 = cp.N_lvl1;
+    const size_t in_s = N1 + 1, out_s = (size_t)2 * cp.ell_lvl1 * 2 * N1;
+    if (threads <= 0) threads = omp_get_max_threads();
+    std::vector<int32_t> in(count * in_s), out(count * out_s);
+    orc_rng rg; orc_rng_seed(&rg, 45);
+    for (auto& v : in) v = (int32_t)orc_rng_u64(&rg);
+    auto pass = [&](int n) {
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+        for (int i = 0; i < n; i++) orc_tfhe_CircuitBootstrapFFT(out.data() + i * out_s, in.data() + i * in_s, K);
+    };
+    pass(threads < count ? threads : count);      // warm-up: per-thread FFT processors, page faults of the 2.7 GB key
+    auto t0 = std::chrono::steady_clock::now();
+    pass(count);
+    double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printf("{\"bench\": \"cb\", \"count\": %d, \"threads\": %d, \"seconds\": %.6f, \"cb_per_s\": %.4f, \"fft\": \"reference spqlios-fma\"}\n",
+           count, threads, dt, count / dt);
+    return 0;
+}
+// 128-bit fixed-point transforms (hp/code.cpp restated, oracle/hpfft_oracle.c) on `threads` cores
+static int cmd_bench_hp(int N, int count, int threads) {
+    const int n = 2 * N;
+    std::vector<orc_cplx96> om(n), ob(n);
+    orc_hp_precomp_iFFT(om.data(), n); orc_hp_precomp_FFT(ob.data(), n);
+    if (threads <= 0) threads = omp_get_max_threads();
+    std::vector<int64_t> in((size_t)count * N), back((size_t)count * N);
+    std::vector<orc_cplx96> spec((size_t)count * (N / 2));
+    orc_rng rg; orc_rng_seed(&rg, 46);
+    for (auto& v : in) v = (int64_t)orc_rng_u64(&rg);
+    auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (int i = 0; i < count; i++) orc_hp_iFFT(spec.data() + (size_t)i * (N / 2), in.data() + (size_t)i * N, n, om.data());
+    double t_i = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (int i = 0; i < count; i++) orc_hp_FFT(back.data() + (size_t)i * N, spec.data() + (size_t)i * (N / 2), n, ob.data());
+    double t_f = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printf("{\"bench\": \"hp\", \"N\": %d, \"count\": %d, \"threads\": %d, \"ifft_per_s\": %.2f, \"fft_per_s\": %.2f}\n", N, count, threads,
+           count / t_i, count / t_f);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 3 && !strcmp(argv[1], "golden")) return cmd_golden(argv[2]);
     if (argc >= 4 && !strcmp(argv[1], "bench-gate")) return cmd_bench_gate(atoi(argv[2]), atoi(argv[3]), argc >= 5 ? atoi(argv[4]) : 1);
+    if (argc >= 4 && !strcmp(argv[1], "bench-cb")) return cmd_bench_cb_mt(atoi(argv[2]), atoi(argv[3]));
     if (argc >= 3 && !strcmp(argv[1], "bench-cb")) return cmd_bench_cb(atoi(argv[2]));
-    fprintf(stderr, "usage: ref_harness golden <dir> | bench-gate <count> <threads> [reps] | bench-cb <count>\n");
+    if (argc >= 5 && !strcmp(argv[1], "bench-hp")) return cmd_bench_hp(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]));
+    fprintf(stderr, "usage: ref_harness golden <dir> | bench-gate <count> <threads> [reps] | bench-cb <count> [threads] | bench-hp <N> <count> <threads>\n");
     return 2;
 }

@@ -249,11 +249,18 @@ class CBOracle:
             lib().orc_preModSwitch(p(out[i]), p(x[i]), self.n0, self.N2)
         return out
 
-    def circuitBootstrapWoKS(self, mu, abar):
+    def circuitBootstrapWoKS(self, mu, abar, threads=1):
         abar = np.ascontiguousarray(abar, np.int32)
         out = np.empty((len(abar), self.N2 + 1), np.int64)
-        for i in range(len(abar)):
+        def one(i):
             lib().orc_circuitBootstrapWoKS(p(out[i]), ctypes.c_int64(mu), p(abar[i]), self.K)
+        if threads > 1:      # ctypes releases the GIL; the oracle functions keep their scratch on the stack / heap per call
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(one, range(len(abar))))
+        else:
+            for i in range(len(abar)):
+                one(i)
         return out
 
     def circuitPrivKS(self, u, x):

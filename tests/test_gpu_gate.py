@@ -291,7 +291,8 @@ def test_key_wire_format_roundtrip(gate_engine, gate_oracle):
 
 def test_two_streams_and_changing_batch_sizes(gate_engine, gate_oracle):
     """Calls are asynchronous on the caller's streams; scratch grows on demand.  Gates issued from two streams with batch sizes that grow and
-    shrink (one CTA's worth, a ragged count, several waves) give the same ciphertexts as the same calls issued one after the other."""
+    shrink (one CTA's worth, a ragged count, several waves) give the same ciphertexts as the same calls issued one after the other
+    (include/tfhe_b200.h "Streams and threads")."""
     g = gate_oracle
     rng = np.random.default_rng(77)
     sizes = [8, 3, 1185, 40, 2500, 9]
@@ -304,18 +305,22 @@ def test_two_streams_and_changing_batch_sizes(gate_engine, gate_oracle):
         gate_engine.bootsGate(op, out, ca, cb, B)
         torch.cuda.synchronize()
         ref.append(out.clone())
-    # NOTE: one context serialises its scratch, so concurrent calls must not share it: streams here interleave submission only
+    # No ordering by the caller: the context orders its scratch users itself (event behind each call's last kernel), so calls
+    # thrown at two streams back to back -- and a host-buffer call in the middle -- must give the same ciphertexts.
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for st in (s1, s2):
+        st.wait_stream(torch.cuda.current_stream())            # inputs were produced on the current stream
     outs = [torch.empty((B, g.n + 1), dtype=torch.int32, device=DEV) for B in sizes]
+    host_out = np.zeros((sizes[2], g.n + 1), np.int32)
     for k, ((ca, cb), B, op) in enumerate(zip(ins, sizes, ops)):
         st = s1 if k % 2 == 0 else s2
-        st.wait_stream(torch.cuda.current_stream())
-        if k > 0:
-            st.wait_stream(s2 if st is s1 else s1)        # the context's scratch is single-buffered: order the calls
         gate_engine.bootsGate(op, outs[k], ca, cb, B, stream=st.cuda_stream)
+        if k == 3:      # a *_host call while device calls are still in flight on both streams
+            gate_engine.bootsGate_host(ops[2], host_out, ins[2][0].cpu().numpy(), ins[2][1].cpu().numpy(), sizes[2])
     s1.synchronize(); s2.synchronize()
     for a, b in zip(outs, ref):
         assert torch.equal(a, b)
+    assert np.array_equal(host_out, ref[2].cpu().numpy())
 
 
 def test_one_process_two_devices(gate_oracle):
