@@ -109,6 +109,7 @@ static void dump(const std::string& dir, const char* name, const void* data, siz
 static int g_fail = 0;
 #define PIN(cond, msg) do { if (!(cond)) { printf("PIN FAILED: %s\n", msg); g_fail++; } else printf("pinned: %s\n", msg); } while (0)
 
+extern "C" int ref_run_pins(const char* golden_dir);
 static int cmd_golden(const std::string& dir) {
     orc_rng r; orc_rng_seed(&r, 2026);
     // ---------------- spqlios transforms vs the portable restatement (same ordering, same conventions)
@@ -238,6 +239,8 @@ static int cmd_golden(const std::string& dir) {
         orc_gate_keys_free(G);
     }
     orc_set_fft_backend(nullptr);
+    // gate-path function bodies and the high-precision FFT of the reference, compiled in place (ref_pins.cpp)
+    g_fail += ref_run_pins(dir.c_str());
     printf("%s\n", g_fail ? "GOLDEN: FAILURES" : "GOLDEN: all pins hold");
     return g_fail ? 1 : 0;
 }

@@ -22,8 +22,30 @@ def load(name, dtype):
 def test_pin_log_is_green():
     log = open(os.path.join(G, "pin_log.txt")).read()
     assert "GOLDEN: all pins hold" in log and "PIN FAILED" not in log
-    for stage in ("preKeySwitch", "preModSwitch", "circuitBootstrapWoKS", "circuitPrivKS", "tfhe_CircuitBootstrapFFT", "Karatsuba"):
-        assert stage in log
+    for stage in ("preKeySwitch", "preModSwitch", "circuitBootstrapWoKS", "circuitPrivKS", "tfhe_CircuitBootstrapFFT", "Karatsuba",
+                  # gate-path function bodies cut out of cb/*_functions.cpp and hp/code.cpp compiled from a patched copy (oracle/ref_pins.cpp)
+                  "modSwitchFromTorus32", "torusPolynomialMulByXaiMinusOne", "tGswTorus32PolynomialDecompH", "tLweExtractLweSampleIndex",
+                  "lweKeySwitchTranslate_fromArray", "hp twiddle tables", "hp iFFT N=2048", "hp FFT N=2048", "hp iFFT N=4096", "hp FFT N=4096"):
+        assert stage in log, stage
+
+
+@pytest.mark.parametrize("N", [2048, 4096])
+def test_hp_oracle_matches_reference_outputs(N):
+    """tests/golden/hp_*: inputs and outputs of the REFERENCE's own iFFT / FFT (hp/code.cpp compiled from a patched copy, NTL twiddle
+    generator replaced by libquadmath).  The oracle reproduces them bit for bit; at N = 4096 the reference's literal `>>10`
+    (:502-503) keeps bits [10,74) where dividing by N/2 keeps [11,75): 63 shared bits."""
+    om, ob = O.hp_tables(N)
+    x = load(f"hp_in_N{N}.i64", np.int64).reshape(-1, N)
+    spec = load(f"hp_spec_N{N}.u64", np.uint64).reshape(len(x), N // 2, 4)
+    back = load(f"hp_back_N{N}.i64", np.int64).reshape(len(x), N)
+    for i in range(len(x)):
+        s = O.hp_iFFT(x[i], N, om)
+        assert np.array_equal(s, spec[i]), f"iFFT polynomial {i}"
+        b = O.hp_FFT(s, N, ob)
+        if N == 2048:
+            assert np.array_equal(b, back[i]), f"FFT polynomial {i}"
+        else:
+            assert np.array_equal(b.view(np.uint64) & np.uint64(2**63 - 1), back[i].view(np.uint64) >> np.uint64(1)), f"FFT polynomial {i}"
 
 
 @pytest.mark.parametrize("N", [1024, 2048])
