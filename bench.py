@@ -402,7 +402,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="gates per GPU per step (default: the BASELINE configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gate-only", action="store_true", help="skip the circuit-bootstrap / hp-FFT / adder sections")
-    ap.add_argument("--adders", type=int, default=2048, help="32-bit adders in total (sharded over the GPUs)")
+    ap.add_argument("--adders", type=int, default=8192, help="32-bit adders in total (sharded over the GPUs)")
     args = ap.parse_args()
     _guard_stdout()
     if args.impl == "reference":

@@ -103,6 +103,9 @@ _SIGS = {
     "tfhe_b200_profile_read": [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)],
     "tfhe_b200_probe_fp64_tflops": [_P, ctypes.POINTER(ctypes.c_double)],
     "tfhe_b200_blindRotate64_FFT_batch": [_P, _P, _P, _I, _P],
+    "tfhe_b200_cb_load_exact_key": [_P, _P],
+    "tfhe_b200_cb_set_exact": [_P, _I],
+    "tfhe_b200_blindRotate64_exact_batch": [_P, _P, _P, _I, _P],
     "tfhe_b200_probe_real96_gprods": [_P, ctypes.POINTER(ctypes.c_double)],
     "tfhe_b200_probe_read_gbs": [_P, ctypes.c_size_t, _I, ctypes.POINTER(ctypes.c_double)],
 }
@@ -368,6 +371,15 @@ class Engine:
 
     def blindRotate64_FFT(self, accum, bara, count, stream=None):
         self._ck(self.lib.tfhe_b200_blindRotate64_FFT_batch(self.h, _ptr(accum), _ptr(bara), count, self._stream(stream)), "blindRotate64_FFT")
+
+    def load_cb_exact_key(self, bk_host):
+        self._ck(self.lib.tfhe_b200_cb_load_exact_key(self.h, _ptr(bk_host)), "cb_load_exact_key")
+
+    def set_cb_exact(self, on):
+        self._ck(self.lib.tfhe_b200_cb_set_exact(self.h, int(bool(on))), "cb_set_exact")
+
+    def blindRotate64_exact(self, accum, bara, count, stream=None):
+        self._ck(self.lib.tfhe_b200_blindRotate64_exact_batch(self.h, _ptr(accum), _ptr(bara), count, self._stream(stream)), "blindRotate64_exact")
 
     def alloc_cb_keys(self, params, with_privks=True):
         p = CBParams(**params) if isinstance(params, dict) else params

@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI of include/tfhe_b200.h: context, key ingestion, batched entry points.
 // No CPU fallback anywhere in this file: every entry point launches sm_100a kernels or fails.
 #include "engine.h"
+#include "exact_ntt.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +28,11 @@ struct tfhe_b200_ctx {
     tfhe_b200_cb_params cp{};
     cplx* c_bkfft = nullptr;
     int32_t* c_preks = nullptr;
+    // exact (NTT) form of the Torus64 bootstrapping key, optional (tfhe_b200_cb_load_exact_key)
+    uint64_t* c_bkntt = nullptr;    // [n0][2 l2][2][2 limbs][N2]
+    uint64_t* ntt_tab = nullptr;    // psi_rev[N2] | psi_inv_rev[N2]
+    uint64_t ntt_n_inv = 0;
+    bool cb_exact = false;          // circuitBootstrapWoKS / CircuitBootstrapFFT use the exact blind rotation
     int32_t* c_privks = nullptr;    // [2][rows][t][base-1][2*N1]
     size_t c_privks_u_stride = 0;   // int32 elements per u
     // hp tables
@@ -159,7 +165,7 @@ int tfhe_b200_ctx_destroy(tfhe_b200_ctx* ctx) {
     if (ctx->scratch_ev) cudaEventDestroy(ctx->scratch_ev);
     cudaFree(ctx->tw1024); cudaFree(ctx->tw2048);
     cudaFree(ctx->g_bkfft); cudaFree(ctx->g_ks);
-    cudaFree(ctx->c_bkfft); cudaFree(ctx->c_preks); cudaFree(ctx->c_privks);
+    cudaFree(ctx->c_bkfft); cudaFree(ctx->c_preks); cudaFree(ctx->c_privks); cudaFree(ctx->c_bkntt); cudaFree(ctx->ntt_tab);
     for (int i = 0; i < 2; i++) { cudaFree(ctx->hp_omega[i]); cudaFree(ctx->hp_ombar[i]); }
     for (int i = 0; i < 4; i++) cudaFree(ctx->scratch[i]);
     delete ctx;
@@ -655,6 +661,7 @@ int tfhe_b200_cb_alloc_keys(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p, in
     ctx->cb_ready = false;
     cudaFree(ctx->c_bkfft); cudaFree(ctx->c_preks); cudaFree(ctx->c_privks);
     ctx->c_bkfft = nullptr; ctx->c_preks = nullptr; ctx->c_privks = nullptr;
+    cudaFree(ctx->c_bkntt); ctx->c_bkntt = nullptr; ctx->cb_exact = false;       // belongs to the previous key
     ctx->cp = *p;
     size_t bytes[3];
     cb_blob_bytes(*p, bytes, &ctx->c_privks_u_stride);
@@ -874,8 +881,21 @@ int tfhe_b200_preModSwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const 
     { ProfScope ps(ctx, 2, (cudaStream_t)stream); CU(launch_modswitch(result_dev, x_dev, 12 /* 2*N2 = 4096 */, (size_t)count * (ctx->cp.n_lvl0 + 1), (cudaStream_t)stream)); }
     return TFHE_B200_OK;
 }
+static ExactArgs exact_args(const tfhe_b200_ctx* ctx, int count) {
+    const tfhe_b200_cb_params& p = ctx->cp;
+    ExactArgs a{};
+    a.key = ctx->c_bkntt; a.psi_rev = ctx->ntt_tab; a.psi_inv_rev = ctx->ntt_tab + p.N_lvl2; a.n_inv = ctx->ntt_n_inv;
+    a.n = p.n_lvl0; a.l = p.ell_lvl2; a.Bgbit = p.bgbit_lvl2; a.count = count; a.out_stride = p.N_lvl2 + 1; a.n_mu = 1;
+    return a;
+}
 static int cb_woks(tfhe_b200_ctx* ctx, int64_t* result_dev, int64_t mu, int n_mu, int mu_bgbit, const int32_t* abar_dev, int count, cudaStream_t s) {
     const tfhe_b200_cb_params& p = ctx->cp;
+    if (ctx->cb_exact) {
+        ExactArgs a = exact_args(ctx, count);
+        a.mode = BR_LWE; a.bara = abar_dev; a.mu = mu; a.n_mu = n_mu; a.mu_bgbit = mu_bgbit; a.out = result_dev;
+        { ProfScope ps(ctx, 0, s); CU(launch_exact_blind_rotate(a, s)); }
+        return TFHE_B200_OK;
+    }
     BRArgs a{};
     a.bkfft = ctx->c_bkfft; a.tw = ctx->tw2048; a.n = p.n_lvl0; a.l = p.ell_lvl2; a.Bgbit = p.bgbit_lvl2; a.count = count;
     a.mode = BR_LWE; a.bara = abar_dev; a.mu = mu; a.n_mu = n_mu; a.mu_bgbit = mu_bgbit; a.out = result_dev; a.out_stride = p.N_lvl2 + 1;
@@ -891,6 +911,46 @@ int tfhe_b200_blindRotate64_FFT_batch(tfhe_b200_ctx* ctx, int64_t* accum_dev, co
     a.bkfft = ctx->c_bkfft; a.tw = ctx->tw2048; a.n = p.n_lvl0; a.l = p.ell_lvl2; a.Bgbit = p.bgbit_lvl2; a.count = count;
     a.mode = BR_ACCUM; a.accum = accum_dev; a.bara = bara_dev; a.n_mu = 1; a.out_stride = p.N_lvl2 + 1;
     { ProfScope ps(ctx, 0, (cudaStream_t)stream); CU(launch_blind_rotate64(a, (cudaStream_t)stream)); }
+    return TFHE_B200_OK;
+}
+/* ---- exact Torus64 path */
+int tfhe_b200_cb_load_exact_key(tfhe_b200_ctx* ctx, const int64_t* bk_host) {
+    NEED_CB(); NEED(bk_host, "cb_load_exact_key: null key");
+    const tfhe_b200_cb_params& p = ctx->cp;
+    const int N2 = p.N_lvl2;
+    NEED(N2 == 2048, "cb_load_exact_key: N_lvl2 must be 2048");
+    // sum over 2l digit polynomials of N terms |digit| <= Bg/2 times a 32-bit limb must stay inside (-p/2, p/2): exact_ntt.cuh
+    NEED(1 + p.ell_lvl2 > 0 && (p.bgbit_lvl2 - 1) + 32 + 11 + 4 <= 62, "cb_load_exact_key: gadget too wide for the limb split");
+    const size_t npoly = (size_t)p.n_lvl0 * 2 * p.ell_lvl2 * 2;
+    if (!ctx->ntt_tab) {
+        std::vector<uint64_t> tab((size_t)2 * N2);
+        gl_make_tables(11, tab.data(), tab.data() + N2, &ctx->ntt_n_inv);
+        CU(cudaMalloc(&ctx->ntt_tab, tab.size() * sizeof(uint64_t)));
+        CU(cudaMemcpy(ctx->ntt_tab, tab.data(), tab.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    if (ctx->c_bkntt) { CU(cudaFree(ctx->c_bkntt)); ctx->c_bkntt = nullptr; }
+    CU(cudaMalloc(&ctx->c_bkntt, npoly * 2 * N2 * sizeof(uint64_t)));
+    int64_t* tmp = nullptr;
+    CU(cudaMalloc(&tmp, npoly * N2 * sizeof(int64_t)));
+    cudaError_t e = cudaMemcpy(tmp, bk_host, npoly * N2 * sizeof(int64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_exact_key(ctx->c_bkntt, tmp, ctx->ntt_tab, N2, npoly, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(tmp);
+    CU(e);
+    return TFHE_B200_OK;
+}
+int tfhe_b200_cb_set_exact(tfhe_b200_ctx* ctx, int on) {
+    NEED_CB();
+    if (on && !ctx->c_bkntt) return fail(ctx, TFHE_B200_ERR_NOKEY, "cb_set_exact: call tfhe_b200_cb_load_exact_key first");
+    ctx->cb_exact = on != 0;
+    return TFHE_B200_OK;
+}
+int tfhe_b200_blindRotate64_exact_batch(tfhe_b200_ctx* ctx, int64_t* accum_dev, const int32_t* bara_dev, int count, void* stream) {
+    NEED_CB(); NEED(count >= 0, "count < 0"); NEED(count == 0 || (accum_dev && bara_dev), "null buffer");
+    if (!ctx->c_bkntt) return fail(ctx, TFHE_B200_ERR_NOKEY, "blindRotate64_exact: call tfhe_b200_cb_load_exact_key first");
+    ExactArgs a = exact_args(ctx, count);
+    a.mode = BR_ACCUM; a.accum = accum_dev; a.bara = bara_dev;
+    { ProfScope ps(ctx, 0, (cudaStream_t)stream); CU(launch_exact_blind_rotate(a, (cudaStream_t)stream)); }
     return TFHE_B200_OK;
 }
 int tfhe_b200_circuitBootstrapWoKS_batch(tfhe_b200_ctx* ctx, int64_t* result_dev, int64_t mu, const int32_t* abar_dev, int count, void* stream) {

@@ -62,6 +62,23 @@ cudaError_t launch_spectrum_to_torus32(int32_t* out, const cplx* in, const cplx*
 cudaError_t launch_spectrum_to_torus64(int64_t* out, const cplx* in, const cplx* tw, int N, int count, double scale, cudaStream_t s);
 cudaError_t launch_spectrum_addmul(cplx* res, const cplx* a, const cplx* b, size_t n_cplx, cudaStream_t s);
 
+// ------------------------------------------------------------------ exact Torus64 blind rotation (exact_kernels.cu, exact_ntt.cuh)
+struct ExactArgs {
+    const uint64_t* key;            // [n][2l][2 q][2 limbs][N] NTT domain (Goldilocks), bit-reversed slots
+    const uint64_t* psi_rev;        // [N]
+    const uint64_t* psi_inv_rev;    // [N]
+    uint64_t n_inv;
+    int n, l, Bgbit, count, mode;   // mode: BR_ACCUM (accum[B][2][N], bara[B][n]) or BR_LWE (bara[B][n+1] -> out[B*n_mu][out_stride])
+    int64_t* accum;
+    const int32_t* bara;
+    int64_t mu;
+    int64_t* out;
+    int out_stride;
+    int n_mu, mu_bgbit;
+};
+cudaError_t launch_exact_key(uint64_t* out, const int64_t* in, const uint64_t* psi_rev, int N, size_t npoly, cudaStream_t s);
+cudaError_t launch_exact_blind_rotate(const ExactArgs& a, cudaStream_t s);
+
 // ------------------------------------------------------------------ key switching (ks_kernels.cu)
 // Device key layout: int32 [rows_in][t][base-1][cols_pad], cols_pad multiple of 512 (d = 0 rows dropped).
 struct KSArgs {

@@ -223,6 +223,15 @@ int tfhe_b200_preModSwitch_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, const 
 /* The blind-rotation loop of circuitBootstrapWoKS alone (:580-642, defects D1/D2 of SURVEY Appendix B corrected) on Torus64
  * accumulators: accum[B][2][N2] in/out, bara[B][n0] in [0, 2*N2).  The Torus64 twin of tfhe_b200_blindRotate_FFT_batch. */
 int tfhe_b200_blindRotate64_FFT_batch(tfhe_b200_ctx* ctx, int64_t* accum_dev, const int32_t* bara_dev, int count, void* stream);
+/* Exact Torus64 path.  The reference's own answers to "the FP64 FFT keeps 53 of ~85 product bits" are its exact
+ * `fake FFT' build (:285-316 -> Karatsuba, cb/poc_karatsuba.cpp:135-206) and the 128-bit FFT (hp/code.cpp:391-512).  Here: a
+ * number-theoretic transform over p = 2^64 - 2^32 + 1 with the key split into two 32-bit limbs; every external product is
+ * bit-identical to the schoolbook product mod 2^64.  load_exact_key takes the same coefficient-domain bk as cb_load_keys (which must
+ * have been called) and builds the NTT-domain key (2x the size of the FP64 spectra); blindRotate64_exact is the exact twin of
+ * blindRotate64_FFT; cb_set_exact(1) makes circuitBootstrapWoKS / CircuitBootstrapFFT run their blind rotations on this path. */
+int tfhe_b200_cb_load_exact_key(tfhe_b200_ctx* ctx, const int64_t* bk_host);
+int tfhe_b200_cb_set_exact(tfhe_b200_ctx* ctx, int on);
+int tfhe_b200_blindRotate64_exact_batch(tfhe_b200_ctx* ctx, int64_t* accum_dev, const int32_t* bara_dev, int count, void* stream);
 /* circuitBootstrapWoKS (:530-659, with the corrections D1-D3 of SURVEY Appendix B):
  * result[B][N2+1] (Torus64), abar[B][n0+1]. */
 int tfhe_b200_circuitBootstrapWoKS_batch(tfhe_b200_ctx* ctx, int64_t* result_dev, int64_t mu,

@@ -145,3 +145,35 @@ def test_bench_engine_arm_refuses_without_gpu():
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_exact_ntt_arithmetic_on_host(tmp_path):
+    """The Goldilocks field arithmetic and the limb-split NTT external product of the exact Torus64 path are __host__ __device__ code
+    (experimental-tfhe_b200/csrc/exact_ntt.cuh): compiled with g++ and checked against 128-bit integer arithmetic and a schoolbook negacyclic product
+    mod 2^64 -- no GPU, no oracle."""
+    exe = str(tmp_path / "ntt_host_check")
+    src = os.path.join(ROOT, "tests", "cpp", "ntt_host_check.cpp")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "experimental-tfhe_b200", "csrc"), "-o", exe, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "NTT HOST CHECK: all ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_ciphertext_wire_format_roundtrip():
+    """tfhe_b200_ciphertext_pack / _unpack are host-side (no device): round trip, damaged payload, truncated blob."""
+    import numpy as np
+    mod = importlib.import_module("experimental-tfhe_b200")
+    rng = np.random.default_rng(2)
+    for kind, arr in (("LWE32", rng.integers(-2**31, 2**31 - 1, size=(5, 501), dtype=np.int64).astype(np.int32)),
+                      ("LWE64", rng.integers(-2**63, 2**63 - 1, size=(3, 2049), dtype=np.int64)),
+                      ("TLWE32", rng.integers(-2**31, 2**31 - 1, size=(2, 2, 1024), dtype=np.int64).astype(np.int32)),
+                      ("TGSW32", rng.integers(-2**31, 2**31 - 1, size=(1, 4, 2, 1024), dtype=np.int64).astype(np.int32))):
+        blob = mod.ciphertext_pack(kind, arr)
+        assert blob.nbytes == 64 + arr.nbytes
+        k2, a2 = mod.ciphertext_unpack(blob)
+        assert k2 == kind and a2.dtype == arr.dtype and np.array_equal(a2, arr)
+        bad = blob.copy(); bad[100] ^= 1
+        with pytest.raises(mod.EngineError, match="checksum"):
+            mod.ciphertext_unpack(bad)
+        with pytest.raises(mod.EngineError, match="size"):
+            mod.ciphertext_unpack(blob[:-8].copy())

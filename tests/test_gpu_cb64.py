@@ -281,3 +281,63 @@ def test_cb_key_blob_roundtrip_and_ciphertext_format(cb_engine, cb_oracle):
         b[70] ^= 0x10
         with pytest.raises(mod.EngineError, match="checksum"):
             mod.ciphertext_unpack(b)
+
+
+def test_exact_ntt_blind_rotation(cb_engine, cb_oracle):
+    """The exact Torus64 path (exact_kernels.cu: Goldilocks NTT, two 32-bit limbs) is BIT-IDENTICAL to the schoolbook external product
+    (orc_tGsw64ExternMulToTLwe_exact = the reference's `fake FFT' build, cb/poc_CircuitBootstrapping.cpp:285-316): single CMUX steps
+    at the wrap-around rotation amounts, several steps in a row, and -- end to end -- circuitBootstrapWoKS decodes with no more noise
+    than the FP64 path."""
+    import json
+    c = cb_oracle
+    N2, n0, l, Bgbit = c.N2, c.n0, c.params.ell_lvl2, c.params.bgbit_lvl2
+    cb_engine.load_cb_exact_key(c.bk)
+    rng = np.random.default_rng(61)
+
+    def oracle_steps(acc, bara_row):
+        acc = acc.copy()
+        for i in np.nonzero(bara_row)[0]:
+            tmp = np.ascontiguousarray(np.stack([mul_by_xai_minus_one(acc[q], int(bara_row[i]), N2) for q in range(2)]))
+            O.lib().orc_tGsw64ExternMulToTLwe_exact(O.p(tmp), O.p(np.ascontiguousarray(c.bk[i])), N2, l, Bgbit)
+            with np.errstate(over="ignore"):
+                acc = acc + tmp
+        return acc
+
+    amounts = [1, 2047, 2048, 2049, 4095, 777]
+    steps = [0, 1, n0 // 2, n0 - 2, n0 - 1, 7]
+    B = len(amounts) + 1
+    acc = rng.integers(-2**63, 2**63 - 1, size=(B, 2, N2), dtype=np.int64)
+    acc[0, 0, :6] = [0, -1, 2**63 - 1, -2**63, 2**27, -2**27]
+    bara = np.zeros((B, n0), np.int32)
+    for b in range(B - 1):
+        bara[b, steps[b]] = amounts[b]
+    bara[B - 1, [3, 100, 499]] = [1234, 4000, 2048]            # three steps in a row
+    d_acc = dev(acc.copy())
+    cb_engine.blindRotate64_exact(d_acc, dev(bara), B)
+    torch.cuda.synchronize()
+    got = d_acc.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(got[b], oracle_steps(acc[b], bara[b])), f"sample {b}: exact path differs from the schoolbook product"
+    # end to end: same inputs through the FP64 and the exact blind rotation
+    Bn = 296
+    bits = rng.integers(0, 2, Bn)
+    x = c.encrypt_lvl1((bits.astype(np.int64) * (1 << 31)).astype(np.int32), 2.0**-20, seed=51)
+    pre = torch.empty((Bn, c.n0 + 1), dtype=torch.int32, device=DEV); abar = torch.empty_like(pre)
+    cb_engine.preKeySwitch(pre, dev(x), Bn); cb_engine.preModSwitch(abar, pre, Bn)
+    mu = 1 << 56
+    expect = np.where(bits != 0, mu, 0).astype(np.int64)
+    res = {}
+    for name, on in (("fp64", 0), ("exact", 1)):
+        cb_engine.set_cb_exact(on)
+        out = torch.empty((Bn, c.N2 + 1), dtype=torch.int64, device=DEV)
+        cb_engine.circuitBootstrapWoKS(out, mu, abar, Bn); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); cb_engine.circuitBootstrapWoKS(out, mu, abar, Bn); e1.record(); torch.cuda.synchronize()
+        err = (c.phase_lvl2(out.cpu().numpy()) - expect).astype(np.float64)
+        res[name] = {"noise_std_log2": float(np.log2(np.sqrt(np.mean(err**2)))), "max_err_log2": float(np.log2(np.abs(err).max())),
+                     "rotations_per_s": Bn / (e0.elapsed_time(e1) * 1e-3), "batch": Bn}
+    cb_engine.set_cb_exact(0)
+    os.makedirs(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out", "exact_vs_fp64.json"), "w"), indent=1)
+    assert res["exact"]["max_err_log2"] < 46 and res["fp64"]["max_err_log2"] < 46
+    assert res["exact"]["noise_std_log2"] <= res["fp64"]["noise_std_log2"] + 0.1, res
