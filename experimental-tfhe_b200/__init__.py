@@ -106,6 +106,7 @@ _SIGS = {
     "tfhe_b200_cb_load_exact_key": [_P, _P],
     "tfhe_b200_cb_set_exact": [_P, _I],
     "tfhe_b200_blindRotate64_exact_batch": [_P, _P, _P, _I, _P],
+    "tfhe_b200_gate_get_params": [_P, ctypes.POINTER(GateParams)],
     "tfhe_b200_probe_real96_gprods": [_P, ctypes.POINTER(ctypes.c_double)],
     "tfhe_b200_probe_read_gbs": [_P, ctypes.c_size_t, _I, ctypes.POINTER(ctypes.c_double)],
 }

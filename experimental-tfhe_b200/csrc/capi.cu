@@ -248,6 +248,12 @@ int tfhe_b200_gate_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p,
     return TFHE_B200_OK;
 }
 
+int tfhe_b200_gate_get_params(const tfhe_b200_ctx* ctx, tfhe_b200_gate_params* p) {
+    if (!ctx || !p) return TFHE_B200_ERR_PARAM;
+    if (!ctx->g_bkfft) return TFHE_B200_ERR_NOKEY;
+    *p = ctx->gp;
+    return TFHE_B200_OK;
+}
 int tfhe_b200_gate_key_blob(tfhe_b200_ctx* ctx, int which, void** dev_ptr, size_t* bytes) {
     if (!ctx) return TFHE_B200_ERR_PARAM;
     NEED(dev_ptr && bytes, "gate_key_blob: null output");

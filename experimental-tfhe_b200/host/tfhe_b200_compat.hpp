@@ -150,11 +150,22 @@ inline void lweKeySwitch_batch(Torus32* result, const LweKeySwitchKey* ks, const
     TFHE_B200_CK(tfhe_b200_lweKeySwitch_batch(ks->engine, dr.p, ds.p, count, nullptr), ks->engine);
     dr.down(result);
 }
+// bkFFT may point INTO the key array (the reference passes bkFFT+i, cb/lwe_functions.cpp:352) and n may be smaller than the key's n:
+// the engine always walks its whole key, so the caller's n rotation amounts are placed at offset bkFFT->index of a zero-padded row
+// (a step with bara = 0 is skipped, :350).  A range that does not fit the key aborts, like the reference's asserts.
 inline void tfhe_blindRotate_FFT_batch(Torus32* accum /*[count][k+1][N]*/, const TGswSampleFFT* bkFFT, const int* bara /*[count][n]*/, int n,
                                        const TGswParams* bk_params, int count) {
     const int N = bk_params->tlwe_params->N;
-    DevBuf<Torus32> da((size_t)count * 2 * N); DevBuf<int> db((size_t)count * n);
-    da.up(accum); db.up(bara);
+    tfhe_b200_gate_params gp;
+    TFHE_B200_CK(tfhe_b200_gate_get_params(bkFFT->engine, &gp), bkFFT->engine);
+    if (n < 0 || bkFFT->index < 0 || bkFFT->index + n > gp.n || N != gp.N) {
+        fprintf(stderr, "tfhe_blindRotate_FFT: steps [%d, %d) do not fit the loaded key (n = %d, N = %d)\n", bkFFT->index, bkFFT->index + n, gp.n, gp.N);
+        abort();
+    }
+    std::vector<int> padded((size_t)count * gp.n, 0);
+    for (int c = 0; c < count; c++) memcpy(padded.data() + (size_t)c * gp.n + bkFFT->index, bara + (size_t)c * n, sizeof(int) * n);
+    DevBuf<Torus32> da((size_t)count * 2 * N); DevBuf<int> db((size_t)count * gp.n);
+    da.up(accum); db.up(padded.data());
     TFHE_B200_CK(tfhe_b200_blindRotate_FFT_batch(bkFFT->engine, da.p, db.p, count, nullptr), bkFFT->engine);
     da.down(accum);
 }
@@ -168,15 +179,12 @@ inline void tfhe_blindRotate_FFT(TLweSample* accum, const TGswSampleFFT* bkFFT, 
     tfhe_blindRotate_FFT_batch(flat.data(), bkFFT, bara, n, bk_params, 1);
     for (int q = 0; q < 2; q++) memcpy(accum->a[q].coefsT, flat.data() + q * N, sizeof(Torus32) * N);
 }
-// tfhe_MuxRotate_FFT (cb/lwe_functions.cpp:328-333): result = accum + bki (x) ((X^barai - 1) accum); bki = bkFFT + i
-inline void tfhe_MuxRotate_FFT(TLweSample* result, const TLweSample* accum, const TGswSampleFFT* bki, const int barai, const TGswParams* bk_params,
-                               int n_total) {
+// tfhe_MuxRotate_FFT (cb/lwe_functions.cpp:328-333), the reference's signature: result = accum + bki (x) ((X^barai - 1) accum); bki = bkFFT + i
+inline void tfhe_MuxRotate_FFT(TLweSample* result, const TLweSample* accum, const TGswSampleFFT* bki, const int barai, const TGswParams* bk_params) {
     const int N = bk_params->tlwe_params->N;
-    std::vector<int> bara(n_total, 0);
-    bara[bki->index] = barai;                      // all other steps have bara = 0, which tfhe_blindRotate_FFT skips (:350)
     for (int q = 0; q < 2; q++) memcpy(result->a[q].coefsT, accum->a[q].coefsT, sizeof(Torus32) * N);
-    const TGswSampleFFT base{bki->engine, 0};
-    tfhe_blindRotate_FFT(result, &base, bara.data(), n_total, bk_params);
+    if (barai == 0) return;                        // (X^0 - 1) accum = 0
+    tfhe_blindRotate_FFT(result, bki, &barai, 1, bk_params);      // one step at the key entry bki points at
 }
 // tfhe_blindRotateAndExtract_FFT (cb/lwe_functions.cpp:366-395)
 inline void tfhe_blindRotateAndExtract_FFT(LweSample* result, const TorusPolynomial* v, const TGswSampleFFT* bk, const int barb, const int* bara,

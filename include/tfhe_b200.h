@@ -79,6 +79,8 @@ int tfhe_b200_gate_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p,
  * device blobs are broadcast (NCCL / cudaMemcpyPeer) by the caller.  which: 0 = bk spectra, 1 = ks. */
 int tfhe_b200_gate_alloc_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p);
 int tfhe_b200_gate_key_blob(tfhe_b200_ctx* ctx, int which, void** dev_ptr, size_t* bytes);
+/* parameters of the gate keys currently allocated / loaded (the reference reaches them through key->params) */
+int tfhe_b200_gate_get_params(const tfhe_b200_ctx* ctx, tfhe_b200_gate_params* p);
 /* The allocated buffers are uninitialised: gates refuse to run (TFHE_B200_ERR_NOKEY) until the caller has filled both blobs and
  * calls this. */
 int tfhe_b200_gate_commit_keys(tfhe_b200_ctx* ctx);

@@ -75,7 +75,7 @@ int main() {
         for (auto& v : flat) v = (Torus32)orc_rng_u64(&r);
         for (int q = 0; q < 2; q++) memcpy(acc.a[q].coefsT, flat.data() + q * gp.N, sizeof(Torus32) * gp.N);
         const int i = 123, barai = 1500;
-        tfhe_MuxRotate_FFT(&res, &acc, bkFFT.bkFFT + i, barai, &bkp, gp.n);
+        tfhe_MuxRotate_FFT(&res, &acc, bkFFT.bkFFT + i, barai, &bkp);          // the reference's own signature (cb/lwe_functions.cpp:328)
         for (int q = 0; q < 2; q++) orc_torusPolynomialMulByXaiMinusOne(tmp.data() + q * gp.N, barai, flat.data() + q * gp.N, gp.N);
         orc_tGswExternMulToTLwe(tmp.data(), K->bk + (size_t)i * bkp.kpl * 2 * gp.N, gp.N, gp.bk_l, gp.bk_Bgbit);
         int worst = 0;
@@ -86,6 +86,17 @@ int main() {
                 if (d > worst) worst = d;
             }
         CHECK(worst <= 1, "tfhe_MuxRotate_FFT within 1 LSB of the exact external product");
+        // tfhe_blindRotate_FFT on a SUB-RANGE of the key, as the reference calls it with bkFFT+i and a shorter n (:352): two steps at
+        // i, i+1 must equal two MuxRotate steps in a row
+        TLweSample two(&accum), ref1(&accum), ref2(&accum);
+        for (int q = 0; q < 2; q++) memcpy(two.a[q].coefsT, flat.data() + q * gp.N, sizeof(Torus32) * gp.N);
+        const int bara2[2] = {barai, 77};
+        tfhe_blindRotate_FFT(&two, bkFFT.bkFFT + i, bara2, 2, &bkp);
+        tfhe_MuxRotate_FFT(&ref1, &acc, bkFFT.bkFFT + i, bara2[0], &bkp);
+        tfhe_MuxRotate_FFT(&ref2, &ref1, bkFFT.bkFFT + i + 1, bara2[1], &bkp);
+        bool same = true;
+        for (int q = 0; q < 2; q++) same = same && memcmp(two.a[q].coefsT, ref2.a[q].coefsT, sizeof(Torus32) * gp.N) == 0;
+        CHECK(same, "tfhe_blindRotate_FFT(bkFFT+i, n=2) == two tfhe_MuxRotate_FFT steps");
     }
     {   // tfhe_bootstrap_woKS_FFT + tfhe_blindRotateAndExtract_FFT: phase == +-mu up to bootstrapping noise
         LweSample x(&in_out), u(&accum.extracted_lweparams);
