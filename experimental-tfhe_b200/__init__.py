@@ -107,6 +107,8 @@ _SIGS = {
     "tfhe_b200_cb_set_exact": [_P, _I],
     "tfhe_b200_blindRotate64_exact_batch": [_P, _P, _P, _I, _P],
     "tfhe_b200_gate_get_params": [_P, ctypes.POINTER(GateParams)],
+    "tfhe_b200_gate_keygen": [_P, ctypes.POINTER(GateParams), ctypes.c_double, ctypes.c_double, ctypes.c_uint64, _P, _P, _P, _P],
+    "tfhe_b200_cb_keygen": [_P, ctypes.POINTER(CBParams), ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_uint64, _P, _P, _P, _I],
     "tfhe_b200_probe_real96_gprods": [_P, ctypes.POINTER(ctypes.c_double)],
     "tfhe_b200_probe_read_gbs": [_P, ctypes.c_size_t, _I, ctypes.POINTER(ctypes.c_double)],
 }
@@ -255,6 +257,26 @@ class Engine:
         p = GateParams(**params) if isinstance(params, dict) else params
         self._ck(self.lib.tfhe_b200_gate_load_keys(self.h, ctypes.byref(p), _ptr(bk_host), _ptr(ks_host)), "gate_load_keys")
         self.gate_params = p
+
+    def gate_keygen(self, params, bk_stdev, ks_stdev, seed, want_raw=False):
+        """Keys generated on the device (tfhe_b200_gate_keygen).  Returns (lwe_key, tlwe_key[, bk_raw, ks_raw]) as numpy arrays."""
+        import numpy as np
+        p = GateParams(**params) if isinstance(params, dict) else params
+        lwe = np.zeros(p.n, np.int32); tlwe = np.zeros(p.N, np.int32)
+        bk = np.zeros((p.n, 2 * p.bk_l, 2, p.N), np.int32) if want_raw else None
+        ks = np.zeros((p.N, p.ks_t, 1 << p.ks_basebit, p.n + 1), np.int32) if want_raw else None
+        self._ck(self.lib.tfhe_b200_gate_keygen(self.h, ctypes.byref(p), bk_stdev, ks_stdev, seed, _ptr(lwe), _ptr(tlwe), _ptr(bk), _ptr(ks)), "gate_keygen")
+        self.gate_params = p
+        return (lwe, tlwe, bk, ks) if want_raw else (lwe, tlwe)
+
+    def cb_keygen(self, params, bkstdev_lvl2, ksstdev_lvl10, ksstdev_lvl21, seed, with_privks=True):
+        import numpy as np
+        p = CBParams(**params) if isinstance(params, dict) else params
+        k0 = np.zeros(p.n_lvl0, np.int32); k1 = np.zeros(p.N_lvl1, np.int32); k2 = np.zeros(p.N_lvl2 + 1, np.int32)
+        self._ck(self.lib.tfhe_b200_cb_keygen(self.h, ctypes.byref(p), bkstdev_lvl2, ksstdev_lvl10, ksstdev_lvl21, seed, _ptr(k0), _ptr(k1), _ptr(k2),
+                                              int(with_privks)), "cb_keygen")
+        self.cb_params = p
+        return k0, k1, k2
 
     def alloc_gate_keys(self, params):
         p = GateParams(**params) if isinstance(params, dict) else params

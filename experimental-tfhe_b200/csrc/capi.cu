@@ -124,6 +124,27 @@ static int upload_tw(tfhe_b200_ctx* ctx, int logM, cplx** dst) {
     return TFHE_B200_OK;
 }
 
+namespace {
+struct DevTmp {           // frees on scope exit
+    void* p = nullptr;
+    ~DevTmp() { if (p) cudaFree(p); }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+uint64_t splitmix64(uint64_t& x) { uint64_t z = (x += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+// uniform binary secret key on the host (client side: it is returned to the caller, never kept)
+void binary_key(int32_t* out, int n, uint64_t& state) { for (int i = 0; i < n; i++) out[i] = (int32_t)(splitmix64(state) >> 63); }
+int upload_key(tfhe_b200_ctx* ctx, DevTmp& bits, DevTmp& idx, int* weight, const int32_t* key, int n) {
+    std::vector<int32_t> set;
+    for (int i = 0; i < n; i++) if (key[i]) set.push_back(i);
+    *weight = (int)set.size();
+    CU(cudaMalloc(&bits.p, sizeof(int32_t) * (size_t)(n > 0 ? n : 1)));
+    CU(cudaMemcpy(bits.p, key, sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&idx.p, sizeof(int32_t) * (set.size() + 1)));
+    if (!set.empty()) CU(cudaMemcpy(idx.p, set.data(), sizeof(int32_t) * set.size(), cudaMemcpyHostToDevice));
+    return TFHE_B200_OK;
+}
+}  // namespace
+
 #pragma GCC visibility push(default)
 extern "C" {
 
@@ -1045,6 +1066,100 @@ int tfhe_b200_CircuitBootstrapFFT_batch_host(tfhe_b200_ctx* ctx, int32_t* result
     CU(cudaStreamSynchronize(ctx->hs[0]));
     CU(cudaStreamSynchronize(ctx->hs[1]));
     ctx->scratch_busy = false;
+    return TFHE_B200_OK;
+}
+
+/* ------------------------------------------------------------------ key generation on the device */
+
+int tfhe_b200_gate_keygen(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p, double bk_stdev, double ks_stdev, uint64_t seed,
+                          int32_t* lwe_key_host, int32_t* tlwe_key_host, int32_t* bk_raw_host, int32_t* ks_raw_host) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(lwe_key_host && tlwe_key_host, "gate_keygen: the secret keys need somewhere to go");
+    NEED(bk_stdev >= 0 && ks_stdev >= 0, "gate_keygen: negative noise");
+    int rc = tfhe_b200_gate_alloc_keys(ctx, p); if (rc) return rc;
+    const int n = p->n, N = p->N, l = p->bk_l, base = 1 << p->ks_basebit;
+    uint64_t st = seed ^ 0x5851F42D4C957F2Dull;
+    binary_key(lwe_key_host, n, st);                       // LweKeyGen cb/lwe_functions.cpp:35-41
+    binary_key(tlwe_key_host, N, st);                      // tLweKeyGen cb/tlwe_functions.cpp:60-68
+    DevTmp s_lwe, i_lwe, s_tlwe, i_tlwe; int w_lwe = 0, w_tlwe = 0;
+    if ((rc = upload_key(ctx, s_lwe, i_lwe, &w_lwe, lwe_key_host, n))) return rc;
+    if ((rc = upload_key(ctx, s_tlwe, i_tlwe, &w_tlwe, tlwe_key_host, N))) return rc;
+    // bk[i] = TGSW(s_i) under the TLWE key (cb/lwe_functions.cpp:504-506), coefficient domain, then the same transform as gate_load_keys
+    const size_t npoly = (size_t)n * 2 * l * 2;
+    DevTmp bk;
+    CU(cudaMalloc(&bk.p, npoly * N * sizeof(int32_t)));
+    CU(launch_tlwe_gadget_keygen32(bk.as<int32_t>(), i_tlwe.as<int32_t>(), w_tlwe, s_lwe.as<int32_t>(), n, l, p->bk_Bgbit, bk_stdev, seed, 1u, 0));
+    CU(launch_poly_to_spectrum32(ctx->g_bkfft, bk.as<int32_t>(), ctx->tw1024, N, (int)npoly, 2.0 / N, 0));
+    if (bk_raw_host) CU(cudaMemcpy(bk_raw_host, bk.p, npoly * N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    // ks[i][j][d] = LWE(s'_i d 2^(32-(j+1)basebit)) under the LWE key (cb/lwe_functions.cpp:113-133)
+    const size_t raw = (size_t)N * p->ks_t * base * (n + 1);
+    DevTmp ks;
+    CU(cudaMalloc(&ks.p, raw * sizeof(int32_t)));
+    CU(launch_lwe_ks_keygen(ks.as<int32_t>(), s_tlwe.as<int32_t>(), s_lwe.as<int32_t>(), N, n, p->ks_t, p->ks_basebit, ks_stdev, seed, 2u, 0));
+    CU(launch_ks_repack(ctx->g_ks, ks.as<int32_t>(), N, p->ks_t, base, n + 1, (int)gate_cols_pad(*p), 0));
+    if (ks_raw_host) CU(cudaMemcpy(ks_raw_host, ks.p, raw * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CU(cudaDeviceSynchronize());
+    ctx->gate_ready = true;
+    return TFHE_B200_OK;
+}
+
+int tfhe_b200_cb_keygen(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p, double bkstdev_lvl2, double ksstdev_lvl10, double ksstdev_lvl21,
+                        uint64_t seed, int32_t* key_lvl0_host, int32_t* key_lvl1_host, int32_t* key_lvl2_host, int with_privks) {
+    if (!ctx) return TFHE_B200_ERR_PARAM;
+    NEED(key_lvl0_host && key_lvl1_host && key_lvl2_host, "cb_keygen: the secret keys need somewhere to go");
+    int rc = tfhe_b200_cb_alloc_keys(ctx, p, with_privks); if (rc) return rc;
+    const int n0 = p->n_lvl0, N1 = p->N_lvl1, N2 = p->N_lvl2, l2 = p->ell_lvl2;
+    uint64_t st = seed ^ 0x2545F4914F6CDD1Dull;
+    binary_key(key_lvl0_host, n0, st);                     // poc:357-369
+    binary_key(key_lvl1_host, N1, st);
+    binary_key(key_lvl2_host, N2, st);
+    key_lvl2_host[N2] = -1;                                // extended key: b is switched like an a-coefficient (:365-367)
+    DevTmp s0, i0, s1, i1, s2, i2; int w0 = 0, w1 = 0, w2 = 0;
+    if ((rc = upload_key(ctx, s0, i0, &w0, key_lvl0_host, n0))) return rc;
+    if ((rc = upload_key(ctx, s1, i1, &w1, key_lvl1_host, N1))) return rc;
+    {   // lvl2 key: N2 binary coefficients as the TLWE64 key, N2 + 1 entries (the last is -1) as the key being switched
+        std::vector<int32_t> set;
+        for (int i = 0; i < N2; i++) if (key_lvl2_host[i]) set.push_back(i);
+        w2 = (int)set.size();
+        CU(cudaMalloc(&s2.p, sizeof(int32_t) * (N2 + 1)));
+        CU(cudaMemcpy(s2.p, key_lvl2_host, sizeof(int32_t) * (N2 + 1), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&i2.p, sizeof(int32_t) * (set.size() + 1)));
+        if (!set.empty()) CU(cudaMemcpy(i2.p, set.data(), sizeof(int32_t) * set.size(), cudaMemcpyHostToDevice));
+    }
+    {   // preKS: LWE(key_lvl1[i] u 2^(32-(j+1)b)) under key_lvl0  (:372-383)
+        const int base = 1 << p->ksbasebit_lvl10, t = p->kslength_lvl10;
+        DevTmp raw;
+        CU(cudaMalloc(&raw.p, (size_t)N1 * t * base * (n0 + 1) * sizeof(int32_t)));
+        CU(launch_lwe_ks_keygen(raw.as<int32_t>(), s1.as<int32_t>(), s0.as<int32_t>(), N1, n0, t, p->ksbasebit_lvl10, ksstdev_lvl10, seed, 3u, 0));
+        CU(launch_ks_repack(ctx->c_preks, raw.as<int32_t>(), N1, t, base, n0 + 1, (int)pad512(n0 + 1), 0));
+        CU(cudaDeviceSynchronize());
+    }
+    {   // bk: TGSW64(key_lvl0[i]) under key_lvl2  (:388-391, tGsw64Encrypt_lvl2 :215-227)
+        const size_t npoly = (size_t)n0 * 2 * l2 * 2;
+        DevTmp raw;
+        CU(cudaMalloc(&raw.p, npoly * N2 * sizeof(int64_t)));
+        CU(launch_tlwe_gadget_keygen64(raw.as<int64_t>(), i2.as<int32_t>(), w2, s0.as<int32_t>(), n0, l2, p->bgbit_lvl2, bkstdev_lvl2, seed, 4u, 0));
+        CU(launch_poly_to_spectrum64(ctx->c_bkfft, raw.as<int64_t>(), ctx->tw2048, N2, (int)npoly, 2.0 / N2, 0));
+        CU(cudaDeviceSynchronize());
+    }
+    if (with_privks) {   // privKS[z][i][j][d] = TLWE32(0) + key_lvl2[i] d 2^(32-(j+1)b) on polynomial z  (:406-419), in slices of input rows
+        const int base = 1 << p->ksbasebit_lvl21, t = p->kslength_lvl21, cols = 2 * N1;
+        const size_t row_raw = (size_t)t * base * cols;                       // int32 per input row i
+        int slice = (int)((size_t)(256u << 20) / (row_raw * sizeof(int32_t)));
+        if (slice < 1) slice = 1;
+        DevTmp raw;
+        CU(cudaMalloc(&raw.p, (size_t)slice * row_raw * sizeof(int32_t)));
+        for (int z = 0; z < 2; z++)
+            for (int r0 = 0; r0 <= N2; r0 += slice) {
+                const int nr = N2 + 1 - r0 < slice ? N2 + 1 - r0 : slice;
+                const size_t row0 = ((size_t)z * (N2 + 1) + r0) * t * base;
+                CU(launch_tlwe_privks_keygen(raw.as<int32_t>(), i1.as<int32_t>(), w1, s2.as<int32_t>(), N2 + 1, t, p->ksbasebit_lvl21, ksstdev_lvl21,
+                                             seed, 5u, row0, (size_t)nr * t * base, 0));
+                CU(launch_ks_repack_rows(ctx->c_privks + (size_t)z * ctx->c_privks_u_stride, raw.as<int32_t>(), N2 + 1, r0, nr, t, base, cols, cols, 0));
+                CU(cudaDeviceSynchronize());
+            }
+    }
+    ctx->cb_ready = true;
     return TFHE_B200_OK;
 }
 

@@ -106,6 +106,17 @@ cudaError_t launch_ks_repack(int32_t* dst, const int32_t* src, int rows, int t, 
 cudaError_t launch_ks_repack_rows(int32_t* dst, const int32_t* src, int rows_total, int row0, int rows, int t, int base, int cols, int cols_pad,
                                   cudaStream_t s);
 
+// ------------------------------------------------------------------ key generation on the device (keygen_kernels.cu)
+// raw host layouts of include/tfhe_b200.h; kidx = indices of the set bits of the binary TLWE key, s = the key being encrypted
+cudaError_t launch_lwe_ks_keygen(int32_t* out, const int32_t* s_in, const int32_t* s_out, int rows_in, int n_out, int t, int basebit, double stdev,
+                                 uint64_t seed, uint32_t stream, cudaStream_t st);
+cudaError_t launch_tlwe_gadget_keygen32(int32_t* out, const int32_t* kidx, int kweight, const int32_t* s, int n, int l, int Bgbit, double stdev,
+                                        uint64_t seed, uint32_t stream, cudaStream_t st);
+cudaError_t launch_tlwe_gadget_keygen64(int64_t* out, const int32_t* kidx, int kweight, const int32_t* s, int n, int l, int Bgbit, double stdev,
+                                        uint64_t seed, uint32_t stream, cudaStream_t st);
+cudaError_t launch_tlwe_privks_keygen(int32_t* out, const int32_t* kidx, int kweight, const int32_t* s, int rows_i, int t, int basebit, double stdev,
+                                      uint64_t seed, uint32_t stream, size_t row0, size_t nrows, cudaStream_t st);
+
 // ------------------------------------------------------------------ small elementwise (misc_kernels.cu)
 cudaError_t launch_lwe_lincomb(int32_t* out, const int32_t* a, const int32_t* b, int ka, int kb, int32_t cconst,
                                int n, int count, cudaStream_t s);   // out = (0,cconst) + ka*a + kb*b   (b may be null)

@@ -248,6 +248,19 @@ int tfhe_b200_CircuitBootstrapFFT_batch_host(tfhe_b200_ctx* ctx, int32_t* result
                                              int count);
 
 /* ------------------------------------------------------------------------------------------------
+ * Key generation on the device.  The reference builds its cloud keys in Globals::Globals
+ * (cb/poc_CircuitBootstrapping.cpp:342-423) on one core in ~100 s; here each key row is one CTA (Philox4x32-10 counters, Box-Muller
+ * Gaussians scaled like cb/generic_utils.h:175-189, exact wrap-around a*K for the TLWE rows) and the keys land in the context ready
+ * to use.  The binary SECRET keys are drawn on the host and handed back to the caller (client side); the context does not keep them.
+ * gate: lwe_key[n], tlwe_key[N]; optional raw copies bk_raw_host[n][2l][2][N], ks_raw_host[N][t][base][n+1] (NULL to skip) for
+ * inspection.  cb: key_lvl0[n0], key_lvl1[N1], key_lvl2[N2+1] (last entry -1, :365-367).
+ * ---------------------------------------------------------------------------------------------- */
+int tfhe_b200_gate_keygen(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p, double bk_stdev, double ks_stdev, uint64_t seed,
+                          int32_t* lwe_key_host, int32_t* tlwe_key_host, int32_t* bk_raw_host, int32_t* ks_raw_host);
+int tfhe_b200_cb_keygen(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p, double bkstdev_lvl2, double ksstdev_lvl10, double ksstdev_lvl21,
+                        uint64_t seed, int32_t* key_lvl0_host, int32_t* key_lvl1_host, int32_t* key_lvl2_host, int with_privks);
+
+/* ------------------------------------------------------------------------------------------------
  * High-precision anticyclic FFT, 128-bit fixed point (hp/code.cpp).  Real96 = value * 2^64 in a
  * wrapping 128-bit integer stored as {lo, hi} 64-bit words (little endian, == unsigned __int128).
  * Complex = {re, im}.  N in {2048, 4096}.
