@@ -425,6 +425,82 @@ __device__ __forceinline__ void cmux_step2(Torus* __restrict__ acc, const int a,
     lanes_sync<T>(bar_id);      // accumulator writes visible before the next step's rotated reads
 }
 
+// ---------------------------------------------------------------------------------------------
+// CEILING PROBE (not a product path; TFHE_B200_BR_VARIANT=m, wrong results by construction): what a warp sustains when it does
+// nothing but the FP64 work of a CMUX -- two digit polynomials at a time, rotated differences "already there" in its tensor-memory
+// columns, key values "already there" in tensor memory too (224..479), results left in tensor memory -- i.e. the compute half of a
+// producer / consumer split in which helper warps would do the integer and key-fetch work.  One such warp per SM sub-partition
+// (4 per SM).  profiles/r2_notes.md has the measurement and what it says about that design.
+// ---------------------------------------------------------------------------------------------
+template <int LOGM>
+__device__ __forceinline__ void cmux_step_mock(const int l, const int Bgbit, cplx* __restrict__ buf, const uint32_t tacc, const uint32_t tkey,
+                                               const uint32_t kstride, const cplx* __restrict__ tw, const int t, const int bar_id, const uint32_t ttw) {
+    const uint32_t mask = (1u << Bgbit) - 1u;
+    const int half = 1 << (Bgbit - 1);
+#pragma unroll 1
+    for (int q = 0; q < 2; q++) {
+        const int sh0 = 32 - Bgbit, sh1 = sh0 - Bgbit;
+        cplx v[16], u[16];
+        {
+            uint32_t w[4][8];
+            tmem_wait_st();
+#pragma unroll
+            for (int c = 0; c < 4; c++) TFHE_TLD8(w[c], tacc + 128 + 8 * c);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t ure = w[c][2 * i], uim = w[c][2 * i + 1];
+                    v[4 * c + i] = make_double2(digit_of(ure, sh0, mask, half), digit_of(uim, sh0, mask, half));
+                    u[4 * c + i] = make_double2(digit_of(ure, sh1, mask, half), digit_of(uim, sh1, mask, half));
+                }
+        }
+        tree_forward2<LOGM, true>(v, u, buf, tw, t, bar_id, ttw);
+        if (q) tmem_wait_st();
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t r0[16], r1[16], k[4][16];
+#pragma unroll
+            for (int x = 0; x < 4; x++) TFHE_TLD16(k[x], tkey + kstride * x + 16 * c);
+            if (q) { TFHE_TLD16(r0, tacc + 16 * c); TFHE_TLD16(r1, tacc + 64 + 16 * c); }
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int s = 4 * c + i;
+                cplx R0 = !q ? make_double2(0.0, 0.0) : make_double2(__hiloint2double((int)r0[4 * i + 1], (int)r0[4 * i]), __hiloint2double((int)r0[4 * i + 3], (int)r0[4 * i + 2]));
+                cplx R1 = !q ? make_double2(0.0, 0.0) : make_double2(__hiloint2double((int)r1[4 * i + 1], (int)r1[4 * i]), __hiloint2double((int)r1[4 * i + 3], (int)r1[4 * i + 2]));
+                cplx kk[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++) kk[x] = make_double2(__hiloint2double((int)k[x][4 * i + 1], (int)k[x][4 * i]), __hiloint2double((int)k[x][4 * i + 3], (int)k[x][4 * i + 2]));
+                cfma(R0, v[s], kk[0]); cfma(R1, v[s], kk[1]); cfma(R0, u[s], kk[2]); cfma(R1, u[s], kk[3]);
+                r0[4 * i] = (uint32_t)__double2loint(R0.x); r0[4 * i + 1] = (uint32_t)__double2hiint(R0.x);
+                r0[4 * i + 2] = (uint32_t)__double2loint(R0.y); r0[4 * i + 3] = (uint32_t)__double2hiint(R0.y);
+                r1[4 * i] = (uint32_t)__double2loint(R1.x); r1[4 * i + 1] = (uint32_t)__double2hiint(R1.x);
+                r1[4 * i + 2] = (uint32_t)__double2loint(R1.y); r1[4 * i + 3] = (uint32_t)__double2hiint(R1.y);
+            }
+            TFHE_TST16(r0, tacc + 16 * c);
+            TFHE_TST16(r1, tacc + 64 + 16 * c);
+        }
+    }
+    {
+        cplx R0[16], R1[16];
+        load_tmem2(R0, R1, tacc);
+        tree_backward2<LOGM, true, true>(R0, R1, buf, tw, t, bar_id, ttw);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t w0[8], w1[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                w0[2 * i] = (uint32_t)double_to_torus32(R0[4 * c + i].x); w0[2 * i + 1] = (uint32_t)double_to_torus32(R0[4 * c + i].y);
+                w1[2 * i] = (uint32_t)double_to_torus32(R1[4 * c + i].x); w1[2 * i + 1] = (uint32_t)double_to_torus32(R1[4 * c + i].y);
+            }
+            TFHE_TST8(w0, tacc + 8 * c);
+            TFHE_TST8(w1, tacc + 64 + 8 * c);
+        }
+    }
+}
+
 // One CMUX: ACC <- ACC + BK_i (x) ((X^a - 1) ACC).   acc: shared [2][N].  bk: BK_i = [2l][2][M] spectra (scaled 2/N).
 // STASH: the rotated difference u = (X^a - 1) ACC_q + offset of a coefficient is formed ONCE per q (level 0: two shared-memory
 // reads, index and sign arithmetic) and parked in this lane's tensor-memory columns [128, 128 + 32 words); levels 1.. only
@@ -683,7 +759,9 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
                 if (KM == KM_TMEM) for (int p = 0; p < 2 * l; p++) { kp.acquire(t & 31); kp.release(t & 31); }     // stay aligned with the key stream
                 continue;
             }
-            if constexpr (F2 > 0) cmux_step2<LOGM, Torus, F2>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, tw, t, bar_id, ttw);
+            if constexpr (F2 == 9) cmux_step_mock<LOGM>(l, A.Bgbit, buf, tacc, tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (GROUPS == 4 ? 224u : 448u),
+                                                        GROUPS == 4 ? 64u : 0u, tw, t, bar_id, ttw);
+            else if constexpr (F2 > 0) cmux_step2<LOGM, Torus, F2>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, tw, t, bar_id, ttw);
             else cmux_step<LOGM, Torus, STASH, KM>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, kp, tw, t, bar_id, ttw);
         }
 
@@ -800,6 +878,8 @@ cudaError_t blind_rotate_init() {
     if ((e = br_attr<9, int32_t, G32, false, KM_REGS2>()) != cudaSuccess) return e;
     if ((e = br_attr<10, int64_t, G64, false, KM_REGS2>()) != cudaSuccess) return e;
     if ((e = br_attr<10, int64_t, G64, true, KM_REGS2>()) != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, 4, true, KM_REGS2, 9>()) != cudaSuccess) return e;
+    if ((e = br_attr<9, int32_t, G32, true, KM_REGS2, 9>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32, true, KM_REGS2, 2>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32, true, KM_REGS2, 3>()) != cudaSuccess) return e;
     if ((e = br_attr<10, int64_t, G64, true, KM_REGS2, 3>()) != cudaSuccess) return e;
@@ -818,6 +898,8 @@ cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
     // "pairs": two digit polynomials per pass (cmux_step2), rolling key window of 2 / 3 slots.  Measured 380 / 382 ms against 354 ms
     // for the default (profiles/r2_notes.md): what the side-by-side transforms gain (short_scoreboard 10.3 -> 5.9 %) the exposed
     // key latency in the multiply-accumulate gives back (long_scoreboard 1.4 -> 7.6 %), and 255 registers leave a few spills.
+    if (variant && variant[0] == 'm') return br_launch<9, int32_t, 4, true, KM_REGS2, 9>(a, a.count, s);           // ceiling probe, 4 warps per SM
+    if (variant && variant[0] == 'M') return br_launch<9, int32_t, G32, true, KM_REGS2, 9>(a, a.count, s);         // ceiling probe, 8 warps per SM
     if (variant && variant[0] == '2') return br_launch<9, int32_t, G32, true, KM_REGS2, 2>(a, a.count, s);
     if (variant && variant[0] == '3') return br_launch<9, int32_t, G32, true, KM_REGS2, 3>(a, a.count, s);
     return br_launch<9, int32_t, G32, true, KM_REGS2>(a, a.count, s);

@@ -667,7 +667,7 @@ static int check_cb_params(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p) {
     NEED(p->ell_lvl1 >= 1 && p->ell_lvl1 <= 4 && p->bgbit_lvl1 >= 1 && p->ell_lvl1 * p->bgbit_lvl1 <= 32, "cb params: bad lvl1 gadget");
     NEED(p->kslength_lvl10 >= 1 && p->kslength_lvl21 >= 1, "cb params: ks length must be >= 1");
     NEED(p->ksbasebit_lvl10 >= 1 && p->ksbasebit_lvl10 <= 3 && p->ksbasebit_lvl21 >= 1 && p->ksbasebit_lvl21 <= 3, "cb params: ks basebit must be 1..3");
-    NEED(p->kslength_lvl10 * p->ksbasebit_lvl10 <= 31 && p->kslength_lvl21 * p->ksbasebit_lvl21 <= 63, "cb params: ks length too large");
+    NEED(p->kslength_lvl10 * p->ksbasebit_lvl10 <= 31 && p->kslength_lvl21 * p->ksbasebit_lvl21 <= 32, "cb params: ks length too large (digits must sit in the top 32 bits)");
     return TFHE_B200_OK;
 }
 // device sizes of the three key blobs: bk spectra, repacked preKS, repacked privKS (both u)

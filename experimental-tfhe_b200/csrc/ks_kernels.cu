@@ -22,6 +22,15 @@ namespace tfhe_b200 {
 #ifndef KS_CTAS
 #define KS_CTAS 2
 #endif
+#ifndef KS_VOTE
+#define KS_VOTE 0             // 1: digit tests through a warp vote (a uniform predicate by construction)
+#endif
+#ifndef KS_NSTAGE4
+#define KS_NSTAGE4 10         // ring depth (blocks) of the base-4 instance
+#endif
+#ifndef KS_UNIFORM
+#define KS_UNIFORM 1          // digits through a warp reduction into uniform registers (see the loop); 0 = round-1 form
+#endif
 constexpr int KS_S = KS_S_DEF;    // samples per thread
 constexpr int KS_TILE = 4 * KS_S; // samples per CTA
 constexpr int KS_ICHUNK = 32;     // input coefficients staged per refill of a warp's digit source
@@ -32,14 +41,14 @@ template <int BASEBIT> struct KSCfg {
     static constexpr int BASE = 1 << BASEBIT;
     static constexpr int STAGE_INTS = (BASE - 1) * 512;            // one (i,j) block: the base-1 candidate rows of this CTA's 512 columns
     static constexpr int STAGE_BYTES = STAGE_INTS * 4;
-    static constexpr int NSTAGE = BASEBIT == 3 ? 6 : (BASEBIT == 2 ? 10 : 16);
+    static constexpr int NSTAGE = BASEBIT == 3 ? 6 : (BASEBIT == 2 ? KS_NSTAGE4 : 16);
     // rows are copied to registers and selected by a warp-uniform branch while base-1 < KS_S; for base 8 there are as many
     // rows as samples per thread, so each sample reads the row it selects straight from the ring instead.
     static constexpr bool ROWS_IN_REGS = BASEBIT <= 2;
 };
 template <typename U, int BASEBIT> constexpr size_t ks_smem_bytes() {
-    return (size_t)KSCfg<BASEBIT>::NSTAGE * KSCfg<BASEBIT>::STAGE_BYTES + 2 * KSCfg<BASEBIT>::NSTAGE * sizeof(uint64_t) +
-           (size_t)KS_WARPS * KS_S * (KS_ICHUNK + 1) * sizeof(U) + 128;
+    return (size_t)KSCfg<BASEBIT>::NSTAGE * KSCfg<BASEBIT>::STAGE_BYTES + KSCfg<BASEBIT>::NSTAGE * sizeof(uint64_t) +
+           (size_t)KSCfg<BASEBIT>::NSTAGE * 32 * sizeof(uint32_t) + (size_t)KS_WARPS * KS_S * (KS_ICHUNK + 1) * sizeof(U) + 128;
 }
 
 __device__ __forceinline__ void sub8(int4& a0, int4& a1, const int4& r0, const int4& r1) {
@@ -72,15 +81,15 @@ __global__ void __launch_bounds__(KS_THREADS, KS_CTAS) keyswitch_kernel(const KS
     extern __shared__ __align__(128) unsigned char ks_smem[];
     int4* ring = reinterpret_cast<int4*>(ks_smem);
     uint64_t* full = reinterpret_cast<uint64_t*>(ks_smem + (size_t)C::NSTAGE * C::STAGE_BYTES);
-    uint32_t* left = reinterpret_cast<uint32_t*>(full + C::NSTAGE);          // warps that have left each slot
-    U* abar_all = reinterpret_cast<U*>(full + 2 * C::NSTAGE);
+    uint32_t* left = reinterpret_cast<uint32_t*>(full + C::NSTAGE);          // [slot][lane]: warps that have left each slot, one copy per lane
+    U* abar_all = reinterpret_cast<U*>(left + C::NSTAGE * 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = A.rows_in * A.t;
     const int32_t* kstream = A.key + (size_t)blockIdx.z * A.key_z_stride + (size_t)blockIdx.y * nblk * C::STAGE_INTS;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::NSTAGE; s++) { mbar_init(full + s, 1); left[s] = 0; }
+        for (int s = 0; s < C::NSTAGE; s++) { mbar_init(full + s, 1); for (int l = 0; l < 32; l++) left[s * 32 + l] = 0; }
         mbar_fence_init();
         for (int s = 0; s < C::NSTAGE && s < nblk; s++) {
             mbar_expect_tx(full + s, C::STAGE_BYTES);
@@ -102,15 +111,20 @@ __global__ void __launch_bounds__(KS_THREADS, KS_CTAS) keyswitch_kernel(const KS
 
     // leave(): count this warp out of a slot (after its reads of the slot have been issued); refill_if_last(): the warp
     // that counted out last refills the slot with the block NSTAGE further on.
+    // Count-out without divergence: every lane increments ITS OWN copy of the slot's counter (32 addresses, one conflict-free
+    // instruction), so all lanes of a warp see the same count and nobody branches.  With `if (lane == 0) atomicAdd` the other 31
+    // lanes waited at the reconvergence point for lane 0's whole atomic round trip -- 18 % of the kernel's stall samples in round 1's
+    // ncu source view (ptxas also wraps a single-lane atom.add in its vote / popc / shuffle aggregation sequence).  Here the result is a
+    // scoreboarded register nobody looks at until refill_if_last, after the block's arithmetic.  atom.inc wraps the counter to 0 on
+    // the last warp by itself, so there is no reset store either.
     auto leave = [&](int slot) -> uint32_t {
-        uint32_t tok = 0;
+        uint32_t tok;
         __syncwarp();
-        if (lane == 0) tok = smem_inc_acq_rel(left + slot);
+        asm volatile("atom.acq_rel.cta.shared::cta.inc.u32 %0, [%1], %2;" : "=r"(tok) : "r"(smem_u32(left + slot * 32 + lane)), "r"(KS_WARPS - 1) : "memory");
         return tok;
     };
     auto refill_if_last = [&](uint32_t tok, int slot, int k) {
-        if (tok == KS_WARPS - 1) {                                // lane 0 of the last warp out
-            left[slot] = 0;
+        if (lane == 0 && tok == KS_WARPS - 1) {                   // lane 0 of the last warp out (the counter has wrapped to 0)
             const int kn = k + C::NSTAGE;
             if (kn < nblk) {
                 fence_proxy_async_smem();
@@ -134,14 +148,23 @@ __global__ void __launch_bounds__(KS_THREADS, KS_CTAS) keyswitch_kernel(const KS
         __syncwarp();
         const int iend = min(KS_ICHUNK, A.rows_in - i0);
         for (int ii = 0; ii < iend; ii++) {
-            U a[KS_S];
+            // The digits of a sample are the same in every lane (all lanes read the same abar entry), but a value loaded from shared
+            // memory is a per-lane value to the compiler: the digit tests became vector compares, divergence brackets (BSSY / BSYNC)
+            // and branch-resolve stalls -- 53 % of the kernel's stall samples sat on that machinery (profiles/r2_notes.md).  A warp
+            // reduction (REDUX writes a UNIFORM register) tells ptxas what we know: everything from here to the branch runs on the
+            // uniform datapath.  Only the top t * basebit <= 32 bits of a coefficient carry digits.
+            uint32_t a[KS_S];
 #pragma unroll
-            for (int s = 0; s < KS_S; s++) a[s] = abar[s][ii];
+            for (int s = 0; s < KS_S; s++) a[s] = KS_UNIFORM == 1 ? __reduce_or_sync(0xffffffffu, (uint32_t)(abar[s][ii] >> (W - 32)))
+                                                                  : (uint32_t)(abar[s][ii] >> (W - 32));
             for (int j = 0; j < A.t; j++, k++) {
-                const int sh = W - (j + 1) * BASEBIT;
+                const int sh = 32 - (j + 1) * BASEBIT;
                 int dg[KS_S];
 #pragma unroll
-                for (int s = 0; s < KS_S; s++) dg[s] = (int)((a[s] >> sh) & (U)(BASE - 1));
+                for (int s = 0; s < KS_S; s++) {
+                    dg[s] = (int)((a[s] >> sh) & (uint32_t)(BASE - 1));
+                    if (KS_UNIFORM == 2) dg[s] = (int)__reduce_or_sync(0xffffffffu, (uint32_t)dg[s]);      // the reduction right in front of the branch
+                }
                 const int4* st = ring + (size_t)slot * (C::STAGE_INTS / 4) + lofs;
                 while (!mbar_try_wait(full + slot, ph)) {}
                 if constexpr (C::ROWS_IN_REGS) {
@@ -153,13 +176,13 @@ __global__ void __launch_bounds__(KS_THREADS, KS_CTAS) keyswitch_kernel(const KS
                     for (int s = 0; s < KS_S; s++) {
 #pragma unroll
                         for (int d = 0; d < BASE - 1; d++)
-                            if (dg[s] == d + 1) sub8(acc0[s], acc1[s], r0[d], r1[d]);      // (predicated subtractions instead: 44.7 vs 36.6 ms)
+                            if (KS_VOTE ? __any_sync(0xffffffffu, dg[s] == d + 1) : (dg[s] == d + 1)) sub8(acc0[s], acc1[s], r0[d], r1[d]);      // (predicated subtractions instead: 44.7 vs 36.6 ms)
                     }
                     refill_if_last(tok, slot, k);
                 } else {
 #pragma unroll
                     for (int s = 0; s < KS_S; s++) {
-                        if (dg[s] != 0) {
+                        if (KS_VOTE ? __any_sync(0xffffffffu, dg[s] != 0) : (dg[s] != 0)) {
                             const int4* rp = st + (dg[s] - 1) * 128;
                             sub8(acc0[s], acc1[s], rp[0], rp[32]);
                         }

@@ -21,8 +21,9 @@ def timeit(fn, reps=3):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
+MODE = sys.argv[2] if len(sys.argv) > 2 else ""
 # ---------------- config 5: hp FFT
-for N in (2048, 4096):
+for N in ((2048, 4096) if MODE != "nohp" else ()):
     B = 16384
     x = torch.randint(-2**63, 2**63 - 1, (B, N), dtype=torch.int64, device="cuda")
     spec = torch.empty((B, N // 2, 4), dtype=torch.int64, device="cuda")
@@ -34,6 +35,8 @@ for N in (2048, 4096):
                            "us_per_iFFT": t_i * 1e3 / B, "roundtrip_max_err_lsb": err}
     print(json.dumps({f"hp_fft_N{N}": out[f"hp_fft_N{N}"]}), flush=True)
 
+if MODE == "hponly":
+    sys.exit(0)
 # ---------------- config 4: circuit bootstrap
 t0 = time.time()
 c = O.CBOracle(seed=42, with_privks=True)
