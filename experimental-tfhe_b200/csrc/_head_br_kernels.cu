@@ -24,10 +24,6 @@
 #include "bk_pipe.cuh"
 #include <cstdlib>
 
-#ifndef BR_FASTDIGIT
-#define BR_FASTDIGIT 1
-#endif
-
 namespace tfhe_b200 {
 
 template <typename Torus> struct TorusTraits;
@@ -519,13 +515,7 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
     typedef typename TorusTraits<Torus>::U U;
     constexpr int M = P::M, N = P::N, T = P::T, W = TorusTraits<Torus>::W;
     constexpr int WPC = StashWords<Torus>::PER_C;
-    // Torus32 digits without mask and bias (FAST32): the field of level lev sits at bits [sh, sh + Bgbit) of u = x + offset and the
-    // digit is field - Bg/2 = the field with its top bit flipped, sign-extended.  Adding 2^(sh+Bgbit-1) flips that bit (the carry leaves
-    // the field upwards), so with 2^31 folded into the offset level 0 is ONE arithmetic shift, and level lev >= 1 is
-    // (int32)(u * 2^(lev Bgbit) + 2^31) >> (32 - Bgbit): the multiply-add moves the field to the top (dropping the 2^31 folded in for level
-    // 0) and flips its top bit.  Same values as ((u >> sh) & mask) - half, two integer instructions fewer per coefficient.
-    constexpr bool FAST32 = sizeof(Torus) == 4 && BR_FASTDIGIT;
-    const U offset = (U)(decomp_offset((U)0, l, Bgbit) + (FAST32 ? (U)0x80000000u : (U)0));
+    const U offset = decomp_offset((U)0, l, Bgbit);
     const uint32_t mask = (1u << Bgbit) - 1u;
     const int half = 1 << (Bgbit - 1);
     const bool stash = STASH && l > 1;
@@ -555,11 +545,6 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
                     if (WPC == 8) { ure = (U)w[c][2 * i]; uim = (U)w[c][2 * i + 1]; }
                     else { ure = (U)(((uint64_t)w[c][(4 * i + 1) % WPC] << 32) | w[c][(4 * i) % WPC]);
                            uim = (U)(((uint64_t)w[c][(4 * i + 3) % WPC] << 32) | w[c][(4 * i + 2) % WPC]); }
-                    if constexpr (FAST32) {
-                        const uint32_t mul = 1u << (lev * Bgbit);
-                        v[4 * c + i] = make_double2((double)((int32_t)((uint32_t)ure * mul + 0x80000000u) >> (32 - Bgbit)),
-                                                    (double)((int32_t)((uint32_t)uim * mul + 0x80000000u) >> (32 - Bgbit)));
-                    } else
                     v[4 * c + i] = make_double2((double)((int)((uint32_t)(ure >> sh) & mask) - half),
                                                 (double)((int)((uint32_t)(uim >> sh) & mask) - half));
                 }
@@ -574,13 +559,6 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
                     const int j = t + T * (4 * c + i);
                     const U ure = (U)(PLAIN ? aq[j] : rot_minus_one<Torus, N>(aq, j, a2)) + offset;
                     const U uim = (U)(PLAIN ? aq[j + M] : rot_minus_one<Torus, N>(aq, j + M, a2)) + offset;
-                    if constexpr (FAST32 && STASH) {          // with a stash this branch only ever sees level 0
-                        v[4 * c + i] = make_double2((double)((int32_t)(uint32_t)ure >> (32 - Bgbit)), (double)((int32_t)(uint32_t)uim >> (32 - Bgbit)));
-                    } else if constexpr (FAST32) {
-                        const uint32_t mul = 1u << (lev * Bgbit), add = lev ? 0x80000000u : 0u;
-                        v[4 * c + i] = make_double2((double)((int32_t)((uint32_t)ure * mul + add) >> (32 - Bgbit)),
-                                                    (double)((int32_t)((uint32_t)uim * mul + add) >> (32 - Bgbit)));
-                    } else
                     v[4 * c + i] = make_double2((double)((int)((uint32_t)(ure >> sh) & mask) - half),
                                                 (double)((int)((uint32_t)(uim >> sh) & mask) - half));
                     if (STASH) {

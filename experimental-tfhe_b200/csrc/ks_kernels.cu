@@ -28,6 +28,9 @@ namespace tfhe_b200 {
 #ifndef KS_NSTAGE4
 #define KS_NSTAGE4 10         // ring depth (blocks) of the base-4 instance
 #endif
+#ifndef KS_LEAVE_DEP
+#define KS_LEAVE_DEP 1        // count-out ordered by operand dependencies instead of a memory barrier (see leave())
+#endif
 #ifndef KS_UNIFORM
 #define KS_UNIFORM 1          // digits through a warp reduction into uniform registers (see the loop); 0 = round-1 form
 #endif
@@ -117,10 +120,24 @@ __global__ void __launch_bounds__(KS_THREADS, KS_CTAS) keyswitch_kernel(const KS
     // ncu source view (ptxas also wraps a single-lane atom.add in its vote / popc / shuffle aggregation sequence).  Here the result is a
     // scoreboarded register nobody looks at until refill_if_last, after the block's arithmetic.  atom.inc wraps the counter to 0 on
     // the last warp by itself, so there is no reset store either.
-    auto leave = [&](int slot) -> uint32_t {
+    // KS_LEAVE_DEP (default): the count-out is a RELAXED atomic that takes the values this lane has just loaded from the slot as (unused)
+    // operands.  What the refill must not overtake is the slot's reads, and a read is over when its destination register is written --
+    // exactly what the operand dependency waits for.  The acq_rel form compiled to MEMBAR.ALL.CTA + ATOMS behind a WARPSYNC: every warp
+    // drained its whole memory pipeline once per block (profiles/r2_notes.md).  The refilling thread still issues fence.proxy.async
+    // between its own count-out and the bulk copy.
+    auto leave = [&](int slot, int dep) -> uint32_t {
         uint32_t tok;
+#if KS_LEAVE_DEP
+        // `dep` is computed from every value loaded from the slot; the volatile move below consumes it, a warp issues in order, so the
+        // atomic cannot issue before those loads have written their registers.
+        int sink;
+        asm volatile("mov.b32 %0, %1;" : "=r"(sink) : "r"(dep));
+        asm volatile("atom.relaxed.cta.shared::cta.inc.u32 %0, [%1], %2;"
+                     : "=r"(tok) : "r"(smem_u32(left + slot * 32 + lane)), "r"(KS_WARPS - 1) : "memory");
+#else
         __syncwarp();
         asm volatile("atom.acq_rel.cta.shared::cta.inc.u32 %0, [%1], %2;" : "=r"(tok) : "r"(smem_u32(left + slot * 32 + lane)), "r"(KS_WARPS - 1) : "memory");
+#endif
         return tok;
     };
     auto refill_if_last = [&](uint32_t tok, int slot, int k) {
@@ -171,7 +188,11 @@ __global__ void __launch_bounds__(KS_THREADS, KS_CTAS) keyswitch_kernel(const KS
                     int4 r0[BASE - 1], r1[BASE - 1];
 #pragma unroll
                     for (int d = 0; d < BASE - 1; d++) { r0[d] = st[d * 128]; r1[d] = st[d * 128 + 32]; }
-                    const uint32_t tok = leave(slot);             // rows are in registers: the slot can be refilled already
+                    // rows are in registers: the slot can be refilled already 
+                    int dep = 0;
+#pragma unroll
+                    for (int d = 0; d < BASE - 1; d++) dep ^= r0[d].x ^ r1[d].w;
+                    const uint32_t tok = leave(slot, dep);
 #pragma unroll
                     for (int s = 0; s < KS_S; s++) {
 #pragma unroll
@@ -180,14 +201,16 @@ __global__ void __launch_bounds__(KS_THREADS, KS_CTAS) keyswitch_kernel(const KS
                     }
                     refill_if_last(tok, slot, k);
                 } else {
+                    int dep = 0;
 #pragma unroll
                     for (int s = 0; s < KS_S; s++) {
                         if (KS_VOTE ? __any_sync(0xffffffffu, dg[s] != 0) : (dg[s] != 0)) {
                             const int4* rp = st + (dg[s] - 1) * 128;
                             sub8(acc0[s], acc1[s], rp[0], rp[32]);
                         }
+                        dep ^= acc0[s].x ^ acc1[s].w;             // (only as an ordering operand of the count-out below)
                     }
-                    refill_if_last(leave(slot), slot, k);
+                    refill_if_last(leave(slot, dep), slot, k);
                 }
                 if (++slot == C::NSTAGE) { slot = 0; ph ^= 1; }
             }
