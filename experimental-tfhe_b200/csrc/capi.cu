@@ -216,6 +216,22 @@ static int check_gate_params(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p)
     return TFHE_B200_OK;
 }
 static size_t gate_cols_pad(const tfhe_b200_gate_params& p) { return (size_t)((p.n + 1 + 511) / 512) * 512; }
+// Device packing of the gate key-switching key.  A base-4 key with an even number of digits is stored PAIRED: two digits = one
+// base-16 digit whose row is the sum of the two rows (ks_kernels.cu) -- 2.5x the bytes, half the blocks and subtractions.
+// TFHE_B200_KS_PAIR=0 keeps the plain packing (development comparison).
+static bool gate_ks_paired(const tfhe_b200_gate_params& p) {
+    static const char* env = getenv("TFHE_B200_KS_PAIR");
+    if (env && env[0] == '0') return false;
+    return p.ks_basebit == 2 && p.ks_t % 2 == 0;
+}
+static size_t gate_ks_bytes(const tfhe_b200_gate_params& p) {
+    const size_t blocks = gate_ks_paired(p) ? (size_t)p.N * (p.ks_t / 2) * 15 : (size_t)p.N * p.ks_t * ((1 << p.ks_basebit) - 1);
+    return blocks * gate_cols_pad(p) * sizeof(int32_t);
+}
+static cudaError_t gate_ks_repack(int32_t* dst, const int32_t* raw_dev, const tfhe_b200_gate_params& p) {
+    if (gate_ks_paired(p)) return launch_ks_repack_pair(dst, raw_dev, p.N, p.ks_t, p.n + 1, (int)gate_cols_pad(p), 0);
+    return launch_ks_repack(dst, raw_dev, p.N, p.ks_t, 1 << p.ks_basebit, p.n + 1, (int)gate_cols_pad(p), 0);
+}
 
 int tfhe_b200_gate_alloc_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p) {
     if (!ctx) return TFHE_B200_ERR_PARAM;
@@ -227,7 +243,7 @@ int tfhe_b200_gate_alloc_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p
     ctx->gp = *p;
     const size_t npoly = (size_t)p->n * 2 * p->bk_l * 2;
     ctx->g_bkfft_bytes = npoly * (p->N / 2) * sizeof(cplx);
-    ctx->g_ks_bytes = (size_t)p->N * p->ks_t * ((1 << p->ks_basebit) - 1) * gate_cols_pad(*p) * sizeof(int32_t);
+    ctx->g_ks_bytes = gate_ks_bytes(*p);
     CU(cudaMalloc(&ctx->g_bkfft, ctx->g_bkfft_bytes));
     CU(cudaMalloc(&ctx->g_ks, ctx->g_ks_bytes));
     // NOT ready yet: the buffers are uninitialised until the caller has filled them (broadcast receiver) and says so with
@@ -261,7 +277,7 @@ int tfhe_b200_gate_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p,
     const size_t raw = (size_t)N * p->ks_t * base * (p->n + 1);
     CU(cudaMalloc(&tmp, raw * sizeof(int32_t)));
     CU(cudaMemcpy(tmp, ks_host, raw * sizeof(int32_t), cudaMemcpyHostToDevice));
-    e = launch_ks_repack(ctx->g_ks, tmp, N, p->ks_t, base, p->n + 1, (int)gate_cols_pad(*p), 0);
+    e = gate_ks_repack(ctx->g_ks, tmp, *p);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaFree(tmp);
     CU(e);
@@ -294,7 +310,7 @@ struct KeyBlobHeader {            // 96 bytes, little endian
     uint64_t reserved[3];
 };
 static_assert(sizeof(KeyBlobHeader) == 96, "wire header is 96 bytes");
-static const uint32_t kKeyBlobVersion = 2;      // bump whenever the spectral slot order or the key-switch packing changes
+static const uint32_t kKeyBlobVersion = 3;      // bump whenever the spectral slot order or the key-switch packing changes
 static uint64_t fnv1a(const unsigned char* p, size_t n, uint64_t h = 1469598103934665603ull) {
     for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
     return h;
@@ -337,7 +353,7 @@ int tfhe_b200_gate_import_keys(tfhe_b200_ctx* ctx, const void* buf_host, size_t 
     // everything about the blob is checked BEFORE the keys currently loaded are released
     int rc = check_gate_params(ctx, &p); if (rc) return rc;
     NEED((size_t)p.n * 2 * p.bk_l * 2 * (p.N / 2) * sizeof(cplx) == h.bk_bytes &&
-         (size_t)p.N * p.ks_t * ((1 << p.ks_basebit) - 1) * gate_cols_pad(p) * sizeof(int32_t) == h.ks_bytes,
+         gate_ks_bytes(p) == h.ks_bytes,
          "gate_import_keys: blob sizes do not match the parameters");
     rc = tfhe_b200_gate_alloc_keys(ctx, &p); if (rc) return rc;
     CU(cudaMemcpy(ctx->g_bkfft, in, h.bk_bytes, cudaMemcpyHostToDevice));
@@ -388,6 +404,7 @@ int tfhe_b200_bootstrap_woKS_FFT_batch(tfhe_b200_ctx* ctx, int32_t* result_dev, 
 static int gate_keyswitch(tfhe_b200_ctx* ctx, int32_t* result_dev, const int32_t* sample_dev, int count, cudaStream_t s) {
     KSArgs k{};
     k.in = sample_dev; k.in_stride = ctx->gp.N + 1; k.rows_in = ctx->gp.N; k.t = ctx->gp.ks_t; k.basebit = ctx->gp.ks_basebit;
+    if (gate_ks_paired(ctx->gp)) { k.t = ctx->gp.ks_t / 2; k.basebit = 4; }      // same digits, taken two at a time
     k.key = ctx->g_ks; k.cols = ctx->gp.n + 1; k.cols_pad = (int)gate_cols_pad(ctx->gp);
     k.b_col = ctx->gp.n; k.b_index = ctx->gp.N; k.out = result_dev; k.out_stride = ctx->gp.n + 1; k.count = count;
     { ProfScope ps(ctx, 1, s); CU(launch_keyswitch32(k, s)); }
@@ -1096,7 +1113,7 @@ int tfhe_b200_gate_keygen(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p, do
     DevTmp ks;
     CU(cudaMalloc(&ks.p, raw * sizeof(int32_t)));
     CU(launch_lwe_ks_keygen(ks.as<int32_t>(), s_tlwe.as<int32_t>(), s_lwe.as<int32_t>(), N, n, p->ks_t, p->ks_basebit, ks_stdev, seed, 2u, 0));
-    CU(launch_ks_repack(ctx->g_ks, ks.as<int32_t>(), N, p->ks_t, base, n + 1, (int)gate_cols_pad(*p), 0));
+    CU(gate_ks_repack(ctx->g_ks, ks.as<int32_t>(), *p));
     if (ks_raw_host) CU(cudaMemcpy(ks_raw_host, ks.p, raw * sizeof(int32_t), cudaMemcpyDeviceToHost));
     CU(cudaDeviceSynchronize());
     ctx->gate_ready = true;

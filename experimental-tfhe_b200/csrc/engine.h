@@ -102,6 +102,8 @@ cudaError_t launch_keyswitch32(const KSArgs& a, cudaStream_t s);
 cudaError_t launch_keyswitch64(const KSArgs& a, cudaStream_t s);
 // raw [rows][t][base][cols] -> device layout
 cudaError_t launch_ks_repack(int32_t* dst, const int32_t* src, int rows, int t, int base, int cols, int cols_pad, cudaStream_t s);
+// paired form of a base-4 key (two digits -> one base-16 digit whose row is the sum of the two rows; ks_kernels.cu), t even
+cudaError_t launch_ks_repack_pair(int32_t* dst, const int32_t* src, int rows, int t, int cols, int cols_pad, cudaStream_t s);
 // the same for a slice [row0, row0 + rows) of rows_total input rows; src holds the slice only
 cudaError_t launch_ks_repack_rows(int32_t* dst, const int32_t* src, int rows_total, int row0, int rows, int t, int base, int cols, int cols_pad,
                                   cudaStream_t s);

@@ -4,9 +4,9 @@
 // (cb/poc_CircuitBootstrapping.cpp:437-465) and circuitPrivKS (:667-698):
 //     result = (0,b) - sum_{i<rows, j<t} key[i][j][ d_ij ],   d_ij = ((a_i + prec_offset) >> (W-(j+1)basebit)) & (base-1), d_ij != 0
 // The reference walks the table once per sample (12.3 MB of rows per gate, 147 MB per private key switch).
-// Here a CTA owns a tile of KS_TILE (32) samples x 512 output columns: every (i,j) block of base-1 candidate rows
+// Here a CTA owns a tile of 32 (KSCfg::TILE) samples x 512 output columns: every (i,j) block of base-1 candidate rows
 // arrives ONCE per CTA (TMA bulk copy into a shared-memory ring) and each sample of the tile subtracts the row its
-// digit selects, so table traffic per sample drops by ~KS_TILE.
+// digit selects, so table traffic per sample drops by ~the tile height.
 //
 // Device key layout: int32 [cols_pad/512][rows][t][base-1][512]  (d = 0 rows are never read by the reference either).
 #include "engine.h"
@@ -31,27 +31,41 @@ namespace tfhe_b200 {
 #ifndef KS_LEAVE_DEP
 #define KS_LEAVE_DEP 1        // count-out ordered by operand dependencies instead of a memory barrier (see leave())
 #endif
+#ifndef KS_NSTAGE16
+#define KS_NSTAGE16 6         // ring depth of the paired (base-16) instance
+#endif
+#ifndef KS_WARPS16
+#define KS_WARPS16 16
+#endif
+#ifndef KS_CTAS16
+#define KS_CTAS16 1
+#endif
 #ifndef KS_UNIFORM
 #define KS_UNIFORM 1          // digits through a warp reduction into uniform registers (see the loop); 0 = round-1 form
 #endif
 constexpr int KS_S = KS_S_DEF;    // samples per thread
-constexpr int KS_TILE = 4 * KS_S; // samples per CTA
 constexpr int KS_ICHUNK = 32;     // input coefficients staged per refill of a warp's digit source
-constexpr int KS_WARPS = 8;       // 4 sample groups x 2 column halves
-constexpr int KS_THREADS = KS_WARPS * 32;
 
+// BASEBIT = 4 is not a parameter set of the reference: it is the PAIRED form of a base-4 key (ks_repack_pair_kernel below), two
+// consecutive base-4 digits of a coefficient taken as one base-16 digit whose row is the sum of the two rows.  Half as many
+// blocks and row subtractions per sample, no compare tree (each sample reads the one row its digit selects); the blocks are
+// 30 KB, so that instance runs 16 warps (64 samples) on a 6-deep ring, one CTA per SM.
 template <int BASEBIT> struct KSCfg {
     static constexpr int BASE = 1 << BASEBIT;
     static constexpr int STAGE_INTS = (BASE - 1) * 512;            // one (i,j) block: the base-1 candidate rows of this CTA's 512 columns
     static constexpr int STAGE_BYTES = STAGE_INTS * 4;
-    static constexpr int NSTAGE = BASEBIT == 3 ? 6 : (BASEBIT == 2 ? KS_NSTAGE4 : 16);
+    static constexpr int NSTAGE = BASEBIT == 4 ? KS_NSTAGE16 : BASEBIT == 3 ? 6 : (BASEBIT == 2 ? KS_NSTAGE4 : 16);
+    static constexpr int WARPS = BASEBIT == 4 ? KS_WARPS16 : 8;    // sample groups x 2 column halves
+    static constexpr int CTAS = BASEBIT == 4 ? KS_CTAS16 : KS_CTAS;
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr int TILE = (WARPS / 2) * KS_S;                // samples per CTA
     // rows are copied to registers and selected by a warp-uniform branch while base-1 < KS_S; for base 8 there are as many
     // rows as samples per thread, so each sample reads the row it selects straight from the ring instead.
     static constexpr bool ROWS_IN_REGS = BASEBIT <= 2;
 };
 template <typename U, int BASEBIT> constexpr size_t ks_smem_bytes() {
     return (size_t)KSCfg<BASEBIT>::NSTAGE * KSCfg<BASEBIT>::STAGE_BYTES + KSCfg<BASEBIT>::NSTAGE * sizeof(uint64_t) +
-           (size_t)KSCfg<BASEBIT>::NSTAGE * 32 * sizeof(uint32_t) + (size_t)KS_WARPS * KS_S * (KS_ICHUNK + 1) * sizeof(U) + 128;
+           (size_t)KSCfg<BASEBIT>::NSTAGE * 32 * sizeof(uint32_t) + (size_t)KSCfg<BASEBIT>::WARPS * KS_S * (KS_ICHUNK + 1) * sizeof(U) + 128;
 }
 
 __device__ __forceinline__ void sub8(int4& a0, int4& a1, const int4& r0, const int4& r1) {
@@ -76,7 +90,7 @@ __device__ __forceinline__ uint32_t smem_inc_acq_rel(uint32_t* p) {
 // a uniform address) and column half w&1; lane l accumulates columns [4l,4l+4) and [128+4l,128+4l+4) of that half -- two
 // conflict-free LDS.128 per row.
 template <typename TorusIn, int BASEBIT>
-__global__ void __launch_bounds__(KS_THREADS, KS_CTAS) keyswitch_kernel(const KSArgs A) {
+__global__ void __launch_bounds__(KSCfg<BASEBIT>::THREADS, KSCfg<BASEBIT>::CTAS) keyswitch_kernel(const KSArgs A) {
     typedef typename std::conditional<sizeof(TorusIn) == 4, uint32_t, uint64_t>::type U;
     typedef KSCfg<BASEBIT> C;
     constexpr int W = sizeof(TorusIn) * 8;
@@ -102,7 +116,7 @@ __global__ void __launch_bounds__(KS_THREADS, KS_CTAS) keyswitch_kernel(const KS
     __syncthreads();
 
     const int sg = warp >> 1, half = warp & 1;
-    const int s0 = blockIdx.x * KS_TILE + sg * KS_S;              // this warp's first sample
+    const int s0 = blockIdx.x * C::TILE + sg * KS_S;              // this warp's first sample
     const TorusIn* in = reinterpret_cast<const TorusIn*>(A.in);
     const U prec_offset = (U)1 << (W - (1 + BASEBIT * A.t));      // cb/lwe_functions.cpp:141 ; poc:444,674
     U (*abar)[KS_ICHUNK + 1] = reinterpret_cast<U (*)[KS_ICHUNK + 1]>(abar_all + (size_t)warp * KS_S * (KS_ICHUNK + 1));
@@ -133,15 +147,15 @@ __global__ void __launch_bounds__(KS_THREADS, KS_CTAS) keyswitch_kernel(const KS
         int sink;
         asm volatile("mov.b32 %0, %1;" : "=r"(sink) : "r"(dep));
         asm volatile("atom.relaxed.cta.shared::cta.inc.u32 %0, [%1], %2;"
-                     : "=r"(tok) : "r"(smem_u32(left + slot * 32 + lane)), "r"(KS_WARPS - 1) : "memory");
+                     : "=r"(tok) : "r"(smem_u32(left + slot * 32 + lane)), "r"(C::WARPS - 1) : "memory");
 #else
         __syncwarp();
-        asm volatile("atom.acq_rel.cta.shared::cta.inc.u32 %0, [%1], %2;" : "=r"(tok) : "r"(smem_u32(left + slot * 32 + lane)), "r"(KS_WARPS - 1) : "memory");
+        asm volatile("atom.acq_rel.cta.shared::cta.inc.u32 %0, [%1], %2;" : "=r"(tok) : "r"(smem_u32(left + slot * 32 + lane)), "r"(C::WARPS - 1) : "memory");
 #endif
         return tok;
     };
     auto refill_if_last = [&](uint32_t tok, int slot, int k) {
-        if (lane == 0 && tok == KS_WARPS - 1) {                   // lane 0 of the last warp out (the counter has wrapped to 0)
+        if (lane == 0 && tok == C::WARPS - 1) {                   // lane 0 of the last warp out (the counter has wrapped to 0)
             const int kn = k + C::NSTAGE;
             if (kn < nblk) {
                 fence_proxy_async_smem();
@@ -248,8 +262,8 @@ static cudaError_t launch_ks_b(const KSArgs& a, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         attr_done.done();
     }
-    dim3 grid((a.count + KS_TILE - 1) / KS_TILE, a.cols_pad / 512, a.nz > 0 ? a.nz : 1);
-    keyswitch_kernel<TorusIn, BASEBIT><<<grid, KS_THREADS, smem, s>>>(a);
+    dim3 grid((a.count + KSCfg<BASEBIT>::TILE - 1) / KSCfg<BASEBIT>::TILE, a.cols_pad / 512, a.nz > 0 ? a.nz : 1);
+    keyswitch_kernel<TorusIn, BASEBIT><<<grid, KSCfg<BASEBIT>::THREADS, smem, s>>>(a);
     return cudaGetLastError();
 }
 template <typename TorusIn>
@@ -261,6 +275,7 @@ static cudaError_t launch_ks(KSArgs a, cudaStream_t s) {
         case 1: return launch_ks_b<TorusIn, 1>(a, s);
         case 2: return launch_ks_b<TorusIn, 2>(a, s);
         case 3: return launch_ks_b<TorusIn, 3>(a, s);
+        case 4: if (sizeof(TorusIn) == 4) return launch_ks_b<int32_t, 4>(a, s); return cudaErrorInvalidValue;      // paired base-4 key (gate path)
         default: return cudaErrorInvalidValue;
     }
 }
@@ -281,6 +296,35 @@ __global__ void ks_repack_kernel(int32_t* __restrict__ dst, const int32_t* __res
         const size_t ij = ro / (base - 1); const int d = (int)(ro % (base - 1)) + 1;
         dst[g * per_group_total + blk0 * (size_t)(base - 1) * 512 + r] = c < cols ? src[(ij * base + d) * (size_t)cols + c] : 0;
     }
+}
+// raw base-4 key [rows][t][4][cols] -> PAIRED layout [cols_pad/512][rows][t/2][15][512]:
+//     row D (1..15) of block (i, jj) = raw[i][2jj][D >> 2] + raw[i][2jj+1][D & 3]   (a zero digit contributes nothing)
+// The key switch subtracts one row per (i, j) with a non-zero digit; subtracting the sum of two rows at once is the same integer
+// arithmetic mod 2^32 in a different order (cb/lwe_functions.cpp:143-151), so results stay bit-identical.
+__global__ void ks_repack_pair_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, size_t rows, int t, int cols, int cols_pad) {
+    const size_t nblk = rows * (size_t)(t / 2);
+    const size_t per_group = nblk * 15 * 512;
+    const size_t total = per_group * (size_t)(cols_pad / 512);
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t g = e / per_group, r = e % per_group;
+        const int c = (int)(g * 512 + r % 512);
+        const size_t ro = r / 512;
+        const size_t blk = ro / 15; const int D = (int)(ro % 15) + 1;
+        const size_t i = blk / (t / 2), jj = blk % (t / 2);
+        const int dh = D >> 2, dl = D & 3;
+        uint32_t v = 0;
+        if (c < cols) {
+            if (dh) v += (uint32_t)src[((i * t + 2 * jj) * 4 + dh) * (size_t)cols + c];
+            if (dl) v += (uint32_t)src[((i * t + 2 * jj + 1) * 4 + dl) * (size_t)cols + c];
+        }
+        dst[e] = (int32_t)v;
+    }
+}
+cudaError_t launch_ks_repack_pair(int32_t* dst, const int32_t* src, int rows, int t, int cols, int cols_pad, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    if (t % 2) return cudaErrorInvalidValue;
+    ks_repack_pair_kernel<<<148 * 8, 256, 0, s>>>(dst, src, (size_t)rows, t, cols, cols_pad);
+    return cudaGetLastError();
 }
 cudaError_t launch_ks_repack_rows(int32_t* dst, const int32_t* src, int rows_total, int row0, int rows, int t, int base, int cols, int cols_pad,
                                   cudaStream_t s) {
