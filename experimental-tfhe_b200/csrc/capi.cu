@@ -222,12 +222,14 @@ static size_t gate_cols_pad(const tfhe_b200_gate_params& p) { return (size_t)((p
 static bool gate_ks_paired(const tfhe_b200_gate_params& p) {
     static const char* env = getenv("TFHE_B200_KS_PAIR");
     if (env && env[0] == '0') return false;
-    return p.ks_basebit == 2 && p.ks_t % 2 == 0;
+    return ks_packing() == KS_PACK_ROWS && p.ks_basebit == 2 && p.ks_t % 2 == 0;
 }
 static size_t gate_ks_bytes(const tfhe_b200_gate_params& p) {
+    if (ks_packing() == KS_PACK_TC) return ks_key_bytes(p.N, p.ks_t, p.ks_basebit, (int)gate_cols_pad(p));
     const size_t blocks = gate_ks_paired(p) ? (size_t)p.N * (p.ks_t / 2) * 15 : (size_t)p.N * p.ks_t * ((1 << p.ks_basebit) - 1);
     return blocks * gate_cols_pad(p) * sizeof(int32_t);
 }
+static int gate_ks_packing_id(const tfhe_b200_gate_params& p) { return ks_packing() == KS_PACK_TC ? 2 : (gate_ks_paired(p) ? 1 : 0); }
 static cudaError_t gate_ks_repack(int32_t* dst, const int32_t* raw_dev, const tfhe_b200_gate_params& p) {
     if (gate_ks_paired(p)) return launch_ks_repack_pair(dst, raw_dev, p.N, p.ks_t, p.n + 1, (int)gate_cols_pad(p), 0);
     return launch_ks_repack(dst, raw_dev, p.N, p.ks_t, 1 << p.ks_basebit, p.n + 1, (int)gate_cols_pad(p), 0);
@@ -305,7 +307,7 @@ int tfhe_b200_gate_key_blob(tfhe_b200_ctx* ctx, int which, void** dev_ptr, size_
 struct KeyBlobHeader {            // 96 bytes, little endian
     char magic[8];                // "TFHEB200"
     uint32_t version, kind;       // kind 1 = gate keys
-    int32_t params[8];            // n, N, k, bk_l, bk_Bgbit, ks_t, ks_basebit, 0
+    int32_t params[8];            // n, N, k, bk_l, bk_Bgbit, ks_t, ks_basebit, packing of the key-switching key (0 rows, 1 paired rows, 2 byte planes)
     uint64_t bk_bytes, ks_bytes, checksum;
     uint64_t reserved[3];
 };
@@ -330,7 +332,7 @@ int tfhe_b200_gate_export_keys(tfhe_b200_ctx* ctx, void* buf_host, size_t* bytes
     memcpy(h.magic, "TFHEB200", 8);
     h.version = kKeyBlobVersion; h.kind = 1;
     const tfhe_b200_gate_params& p = ctx->gp;
-    const int32_t pv[8] = {p.n, p.N, p.k, p.bk_l, p.bk_Bgbit, p.ks_t, p.ks_basebit, 0};
+    const int32_t pv[8] = {p.n, p.N, p.k, p.bk_l, p.bk_Bgbit, p.ks_t, p.ks_basebit, gate_ks_packing_id(p)};
     memcpy(h.params, pv, sizeof(pv));
     h.bk_bytes = ctx->g_bkfft_bytes; h.ks_bytes = ctx->g_ks_bytes;
     h.checksum = fnv1a(out + sizeof(KeyBlobHeader), ctx->g_bkfft_bytes + ctx->g_ks_bytes);
@@ -352,6 +354,7 @@ int tfhe_b200_gate_import_keys(tfhe_b200_ctx* ctx, const void* buf_host, size_t 
     tfhe_b200_gate_params p{h.params[0], h.params[1], h.params[2], h.params[3], h.params[4], h.params[5], h.params[6]};
     // everything about the blob is checked BEFORE the keys currently loaded are released
     int rc = check_gate_params(ctx, &p); if (rc) return rc;
+    NEED(h.params[7] == gate_ks_packing_id(p), "gate_import_keys: the blob's key-switching key is in another packing (TFHE_B200_KS / TFHE_B200_KS_PAIR differ)");
     NEED((size_t)p.n * 2 * p.bk_l * 2 * (p.N / 2) * sizeof(cplx) == h.bk_bytes &&
          gate_ks_bytes(p) == h.ks_bytes,
          "gate_import_keys: blob sizes do not match the parameters");
@@ -690,8 +693,8 @@ static int check_cb_params(tfhe_b200_ctx* ctx, const tfhe_b200_cb_params* p) {
 // device sizes of the three key blobs: bk spectra, repacked preKS, repacked privKS (both u)
 static void cb_blob_bytes(const tfhe_b200_cb_params& p, size_t out[3], size_t* privks_u_stride) {
     out[0] = (size_t)p.n_lvl0 * 2 * p.ell_lvl2 * 2 * (p.N_lvl2 / 2) * sizeof(cplx);
-    out[1] = (size_t)p.N_lvl1 * p.kslength_lvl10 * ((1 << p.ksbasebit_lvl10) - 1) * pad512(p.n_lvl0 + 1) * sizeof(int32_t);
-    const size_t us = (size_t)(p.N_lvl2 + 1) * p.kslength_lvl21 * ((1 << p.ksbasebit_lvl21) - 1) * 2 * p.N_lvl1;
+    out[1] = ks_key_bytes(p.N_lvl1, p.kslength_lvl10, p.ksbasebit_lvl10, (int)pad512(p.n_lvl0 + 1));
+    const size_t us = ks_key_bytes(p.N_lvl2 + 1, p.kslength_lvl21, p.ksbasebit_lvl21, 2 * p.N_lvl1) / sizeof(int32_t);
     out[2] = 2 * us * sizeof(int32_t);
     if (privks_u_stride) *privks_u_stride = us;
 }

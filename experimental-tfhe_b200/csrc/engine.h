@@ -98,6 +98,13 @@ struct KSArgs {
     int group, out_inner;
     int nz; size_t key_z_stride, out_z_stride;
 };
+// Two packings of a key-switching key, chosen once per process (TFHE_B200_KS=cuda selects the first; default is the second):
+//   KS_PACK_ROWS: int32 rows for the CUDA-core kernels (ks_kernels.cu): [cols_pad/512][rows][t][base-1][512]
+//   KS_PACK_TC  : byte-plane images for the tensor-core kernel (ks_tc_kernels.cu): [cols_pad/128][step][plane][4096 B]
+// launch_ks_repack* build the active packing, launch_keyswitch* run the matching kernel, ks_key_bytes sizes the buffer.
+enum KSPacking { KS_PACK_ROWS = 0, KS_PACK_TC = 1 };
+int ks_packing();
+size_t ks_key_bytes(int rows, int t, int basebit, int cols_pad);
 cudaError_t launch_keyswitch32(const KSArgs& a, cudaStream_t s);
 cudaError_t launch_keyswitch64(const KSArgs& a, cudaStream_t s);
 // raw [rows][t][base][cols] -> device layout

@@ -40,6 +40,15 @@ namespace tfhe_b200 {
 #ifndef KS_CTAS16
 #define KS_CTAS16 1
 #endif
+#ifndef KS_NSTAGE8
+#define KS_NSTAGE8 6          // base-8 instance (private key switch of the circuit bootstrap): ring depth, warps per CTA, CTAs per SM
+#endif
+#ifndef KS_WARPS8
+#define KS_WARPS8 8
+#endif
+#ifndef KS_CTAS8
+#define KS_CTAS8 2
+#endif
 #ifndef KS_UNIFORM
 #define KS_UNIFORM 1          // digits through a warp reduction into uniform registers (see the loop); 0 = round-1 form
 #endif
@@ -54,9 +63,9 @@ template <int BASEBIT> struct KSCfg {
     static constexpr int BASE = 1 << BASEBIT;
     static constexpr int STAGE_INTS = (BASE - 1) * 512;            // one (i,j) block: the base-1 candidate rows of this CTA's 512 columns
     static constexpr int STAGE_BYTES = STAGE_INTS * 4;
-    static constexpr int NSTAGE = BASEBIT == 4 ? KS_NSTAGE16 : BASEBIT == 3 ? 6 : (BASEBIT == 2 ? KS_NSTAGE4 : 16);
-    static constexpr int WARPS = BASEBIT == 4 ? KS_WARPS16 : 8;    // sample groups x 2 column halves
-    static constexpr int CTAS = BASEBIT == 4 ? KS_CTAS16 : KS_CTAS;
+    static constexpr int NSTAGE = BASEBIT == 4 ? KS_NSTAGE16 : BASEBIT == 3 ? KS_NSTAGE8 : (BASEBIT == 2 ? KS_NSTAGE4 : 16);
+    static constexpr int WARPS = BASEBIT == 4 ? KS_WARPS16 : BASEBIT == 3 ? KS_WARPS8 : 8;    // sample groups x 2 column halves
+    static constexpr int CTAS = BASEBIT == 4 ? KS_CTAS16 : BASEBIT == 3 ? KS_CTAS8 : KS_CTAS;
     static constexpr int THREADS = WARPS * 32;
     static constexpr int TILE = (WARPS / 2) * KS_S;                // samples per CTA
     // rows are copied to registers and selected by a warp-uniform branch while base-1 < KS_S; for base 8 there are as many
@@ -279,8 +288,8 @@ static cudaError_t launch_ks(KSArgs a, cudaStream_t s) {
         default: return cudaErrorInvalidValue;
     }
 }
-cudaError_t launch_keyswitch32(const KSArgs& a, cudaStream_t s) { return launch_ks<int32_t>(a, s); }
-cudaError_t launch_keyswitch64(const KSArgs& a, cudaStream_t s) { return launch_ks<int64_t>(a, s); }
+cudaError_t launch_keyswitch32_rows(const KSArgs& a, cudaStream_t s) { return launch_ks<int32_t>(a, s); }
+cudaError_t launch_keyswitch64_rows(const KSArgs& a, cudaStream_t s) { return launch_ks<int64_t>(a, s); }
 
 // raw [rows][t][base][cols] -> [cols_pad/512][rows][t][base-1][512]  (d = 0 dropped, zero padded).  src holds the blocks
 // [blk0, blk0 + nblk) of nblk_total (a slice of input rows): large keys are staged through a small temporary.
@@ -326,14 +335,12 @@ cudaError_t launch_ks_repack_pair(int32_t* dst, const int32_t* src, int rows, in
     ks_repack_pair_kernel<<<148 * 8, 256, 0, s>>>(dst, src, (size_t)rows, t, cols, cols_pad);
     return cudaGetLastError();
 }
-cudaError_t launch_ks_repack_rows(int32_t* dst, const int32_t* src, int rows_total, int row0, int rows, int t, int base, int cols, int cols_pad,
-                                  cudaStream_t s) {
+cudaError_t launch_ks_repack_rows_rows(int32_t* dst, const int32_t* src, int rows_total, int row0, int rows, int t, int base, int cols, int cols_pad,
+                                       cudaStream_t s) {
     if (rows <= 0) return cudaSuccess;
     ks_repack_kernel<<<148 * 8, 256, 0, s>>>(dst, src, (size_t)rows_total * t, (size_t)row0 * t, (size_t)rows * t, base, cols, cols_pad);
     return cudaGetLastError();
 }
-cudaError_t launch_ks_repack(int32_t* dst, const int32_t* src, int rows, int t, int base, int cols, int cols_pad, cudaStream_t s) {
-    return launch_ks_repack_rows(dst, src, rows, 0, rows, t, base, cols, cols_pad, s);
-}
+// (launch_ks_repack, launch_ks_repack_rows, launch_keyswitch32/64: the dispatching entry points live in ks_tc_kernels.cu)
 
 }  // namespace tfhe_b200

@@ -8,7 +8,7 @@ mkdir -p ../tools/alt build
 nvcc -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
      -Xptxas -v $FLAGS -c csrc/${SRCTU:-$TU}.cu -o build/alt_${NAME}_$TU.o 2> build/alt_${NAME}_$TU.ptxas.log || (cat build/alt_${NAME}_$TU.ptxas.log; false)
 OBJS=""
-for o in capi br_kernels ks_kernels misc_kernels hp_kernels exact_kernels keygen_kernels twiddles; do
+for o in capi br_kernels ks_kernels ks_tc_kernels misc_kernels hp_kernels exact_kernels keygen_kernels twiddles; do
   if [ "$o" == "$TU" ]; then OBJS="$OBJS build/alt_${NAME}_$TU.o"; else OBJS="$OBJS build/$o.o"; fi
 done
 nvcc -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -shared -o ../tools/alt/libtfhe_b200_$NAME.so $OBJS -lquadmath -cudart static
