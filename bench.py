@@ -112,6 +112,31 @@ FLOP_PER_CB = 704.512e6          # 2 blind rotations x 500 CMUX x 704
 CB_BATCH = 4096
 
 
+def _tensor_peak_tops():
+    """int8 dense peak = 2 x the bf16 dense peak (same tensor cores, half the operand width); the bf16 figure is the measured one
+    of MEASURED_PEAKS.json (sustained: the key switch runs inside a long step), else the profiling recipe's nominal 2250."""
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return 2.0 * float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"])), "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 = 2 x bf16 rate)"
+    except Exception:
+        return 4500.0, "fallback: nominal 4.5 POP/s int8 dense (B200_PROFILING.md)"
+
+
+def _ks_tensor_roofline(kernel, samples, rows, t, basebit, cols_pad, nz, ms):
+    """One-hot GEMM of a key switch on the tensor cores (csrc/ks_tc_kernels.cu): per sample, step and output column 32 rows x 4 byte
+    planes of u8 x u8 multiply-accumulates are issued; only 1 in 2^basebit rows of the one-hot operand is non-zero, so the USEFUL
+    integer additions (the reference's count) are given next to the issued tensor operations."""
+    q = 32 // (1 << basebit)
+    steps = (rows * t + q - 1) // q
+    macs = float(samples) * nz * steps * 32 * 4 * cols_pad
+    peak, src = _tensor_peak_tops()
+    ach = 2.0 * macs / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "TOP/s", "frac": ach / peak, "peak_source": src,
+            "traffic": None, "key_image_bytes": nz * (cols_pad // 128) * steps * 16384,
+            "useful_int32_adds": float(samples) * nz * rows * t * (1.0 - 2.0 ** -basebit) * cols_pad,
+            "algorithmic": "u8 x u8 -> s32 MACs issued: samples x steps x 32 rows x 4 byte planes x padded columns (one-hot operand)"}
+
+
 def _traffic(kernel):
     for name in ("r2_traffic.json", "r1_traffic.json"):
         try:
@@ -191,12 +216,13 @@ def section_circuit_bootstrap(torch, np, eng, par, dist, rank, world, dev, fp64_
                         "traffic": tr_br["dram_bytes_per_launch"] if tr_br and tr_br.get("batch") == B else None,
                         "traffic_source": tr_br["source"] if tr_br and tr_br.get("batch") == B else None,
                         "algorithmic": "704.5 MFLOP per circuit bootstrap (both mu_w in one launch: 8192 rotations of 352.3 MFLOP)"},
-           "privks": {"kernel": "keyswitch_kernel<int64_t,3> (4 private key switches, one launch)", "ms": ks_ms,
-                      "table_bytes": 2 * (p["N_lvl2"] + 1) * p["kslength_lvl21"] * 7 * 2 * p["N_lvl1"] * 4,
-                      "int32_adds_per_cb": 146.9e6,
+           "privks": {"kernel": "keyswitch_tc_kernel<int64_t,3> (4 private key switches, one launch) + keyswitch_tc_kernel<int32_t,2> (preKS)",
+                      "ms": ks_ms, "int32_adds_per_cb": 146.9e6,
+                      "roofline": _ks_tensor_roofline("keyswitch_tc_kernel<int64_t,3>", B * p["ell_lvl1"], p["N_lvl2"] + 1, p["kslength_lvl21"],
+                                                      p["ksbasebit_lvl21"], 2 * p["N_lvl1"], 2, ks_ms),
                       "traffic": tr_ks["dram_bytes_per_launch"] if tr_ks and tr_ks.get("batch") == B else None,
                       "traffic_source": tr_ks["source"] if tr_ks and tr_ks.get("batch") == B else None},
-           "key_replication_ms": t_rep * 1e3, "key_bytes_replicated": 131072000 + 37748736 + 2349858816, "host_keygen_s": t_gen,
+           "key_replication_ms": t_rep * 1e3, "key_bytes_replicated": int(sum(eng.cb_key_blob(w)[1] for w in (0, 1, 2))), "host_keygen_s": t_gen,
            "gpu_launches": int(sum(kern_n.values()))}
     if cpu_baseline and world == 1:
         threads = host_threads()
@@ -532,12 +558,10 @@ def main():
         # DRAM bytes per launch of the blind-rotation kernel, from the committed ncu --set full capture of this same command
         # (profiles/r1_traffic.json says which report); only quoted when the capture was taken at this batch size
         traffic, traffic_src = None, None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["blind_rotate_kernel"]
-            if tr["batch"] == B:
-                traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
-        except Exception:
-            pass
+        tr = _traffic("blind_rotate_kernel")
+        if tr and tr.get("batch") == B:
+            traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
+        ks_ms = kern_ms["keyswitch"] / max(kern_n["keyswitch"], 1)
         line = {
             "metric": METRIC, "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -553,6 +577,7 @@ def main():
                          "peak_source": "DFMA probe measured in this run (nominal 37.2 at 1965 MHz)",
                          "algorithmic": "94.72 MFLOP per gate bootstrap x gates per launch (SURVEY 8d)",
                          "l2_read_gbs_measured": l2_gbs},
+            "roofline_keyswitch": _ks_tensor_roofline("keyswitch_tc_kernel<int32_t,2>", B, 1024, 8, 2, 512, 1, ks_ms),
             "roofline_l2": {"bound": "l2", "achieved": 32.768e6 * B / (br_ms * 1e-3) / 1e9, "peak": l2_gbs, "unit": "GB/s",
                             "note": "bootstrapping-key stream, 32.77 MB per bootstrap per accumulator (SURVEY 8d), against the L2 read "
                                     "bandwidth measured in this run: the co-bound of the FP64 roofline, not the limiter"},
@@ -562,7 +587,7 @@ def main():
             "clocks": clocks,
             "strong": {"scaling": "strong", "value": B / (strong_ms * 1e-3), "unit": "gates/s", "ms_per_step": strong_ms,
                        "config": {"workload": f"{B} bootsNAND in total, sharded {world} ways", "gates_per_gpu": sB}},
-            "key_replication_ms": gate_key_ms, "key_bytes_replicated": 32768000 + 50331648,
+            "key_replication_ms": gate_key_ms, "key_bytes_replicated": int(sum(eng.gate_key_blob(w)[1] for w in (0, 1))),
         }
         line.update({k: v for k, v in extra.items() if v is not None})
         if not args.no_cpu_baseline and world == 1:
