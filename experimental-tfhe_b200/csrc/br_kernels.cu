@@ -650,172 +650,6 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
     TL(15);
 }
 
-// ---------------------------------------------------------------------------------------------
-// One CMUX with DEFERRED multiply-accumulates (TFHE_B200_BR_VARIANT=d; Torus32, 8 warps).  In cmux_step a warp alternates between
-// phases that keep the FP64 pipe busy (the passes) and phases that only wait -- on the load/store unit (the transpose: ~500 of its
-// ~700 cycles are queueing and latency, ncu source view) or on tensor memory (the multiply-accumulate: 128 DFMAs in ~730 cycles).
-// Here the spectrum of digit polynomial p is parked in 64 tensor-memory columns after its last stage, and its multiply-accumulates
-// run INSIDE the transpose of polynomial p+1, chunk by chunk between the transpose's loads: two latency-bound phases on different
-// units overlap instead of following each other.  The key values of polynomial p are requested before pass A of p+1 and consumed
-// in its transpose, so they are not live during pass B / the exchange any more.  The last polynomial has no successor: its
-// multiply-accumulates run right behind its last stage, as before.  The accumulators are zeroed at the start of the CMUX so that
-// every multiply-accumulate is the same code.
-// Tensor memory per lane quarter (two warps): [R0 64 | R1 64 | stash 32 | spectrum 64] x 2 | twiddles 64 (the same for both warps:
-// they depend on the lane only) = 512 columns.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ cplx unpack_cplx(const uint32_t (&r)[16], const int i) {
-    return make_double2(__hiloint2double((int)r[4 * i + 1], (int)r[4 * i]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]));
-}
-__device__ __forceinline__ void pack_cplx(uint32_t (&r)[16], const int i, const cplx x) {
-    r[4 * i] = (uint32_t)__double2loint(x.x); r[4 * i + 1] = (uint32_t)__double2hiint(x.x);
-    r[4 * i + 2] = (uint32_t)__double2loint(x.y); r[4 * i + 3] = (uint32_t)__double2hiint(x.y);
-}
-template <int LOGM, typename Torus, bool PLAIN = false>
-__device__ __forceinline__ void cmux_step_deferred(Torus* __restrict__ acc, const int a, const cplx* __restrict__ bk,
-                                                   const int l, const int Bgbit, cplx* __restrict__ buf, const uint32_t tacc,
-                                                   const cplx* __restrict__ tw, const int t, const int bar_id, const uint32_t ttw) {
-    typedef TreePlan<LOGM> P;
-    typedef typename TorusTraits<Torus>::U U;
-    static_assert(sizeof(Torus) == 4, "deferred variant: Torus32 only");
-    constexpr int M = P::M, N = P::N, T = P::T;
-    const uint32_t tstash = tacc + 128u, tspec = tacc + 160u;
-    const U offset = (U)(decomp_offset((U)0, l, Bgbit) + (U)0x80000000u);          // FAST32 digits (see cmux_step)
-    const int last = 2 * l - 1;
-    {   // R0 = R1 = 0
-        uint32_t z[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) z[i] = 0u;
-#pragma unroll
-        for (int c = 0; c < 8; c++) TFHE_TST16(z, tacc + 16 * c);
-    }
-#pragma unroll 1
-    for (int p = 0; p <= last; p++) {
-        const int q = p >= l, lev = p - q * l;
-        const Torus* __restrict__ aq = acc + q * N;
-        cplx v[16];
-        // ---- digits of this polynomial
-        if (lev > 0) {
-            uint32_t w[4][8];
-            tmem_wait_st();
-#pragma unroll
-            for (int c = 0; c < 4; c++) TFHE_TLD8(w[c], tstash + 8 * c);
-            tmem_wait_ld();
-            const uint32_t mul = 1u << (lev * Bgbit);
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    v[4 * c + i] = make_double2((double)((int32_t)(w[c][2 * i] * mul + 0x80000000u) >> (32 - Bgbit)),
-                                                (double)((int32_t)(w[c][2 * i + 1] * mul + 0x80000000u) >> (32 - Bgbit)));
-        } else {
-            int a2 = a;
-            asm volatile("" : "+r"(a2));          // keep the 32 rotated addresses from being hoisted out of the loop
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                uint32_t w[8];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int j = t + T * (4 * c + i);
-                    const U ure = (U)(PLAIN ? aq[j] : rot_minus_one<Torus, N>(aq, j, a2)) + offset;
-                    const U uim = (U)(PLAIN ? aq[j + M] : rot_minus_one<Torus, N>(aq, j + M, a2)) + offset;
-                    v[4 * c + i] = make_double2((double)((int32_t)ure >> (32 - Bgbit)), (double)((int32_t)uim >> (32 - Bgbit)));
-                    w[2 * i] = (uint32_t)ure; w[2 * i + 1] = (uint32_t)uim;
-                }
-                if (l > 1) TFHE_TST8(w, tstash + 8 * c);
-            }
-        }
-        // ---- depths 0-3
-        pass16<false>(v, reinterpret_cast<const cplx*>(c_tree_ta), 1);
-        // ---- transpose write
-        lanes_sync<T>(bar_id);                                   // WAR: earlier reads of buf
-#pragma unroll
-        for (int m = 0; m < 16; m++) buf[m * P::S + t] = v[m];
-        // ---- key values of the PREVIOUS polynomial: requested once the pass's registers are free (v is in shared memory now),
-        //      consumed inside this polynomial's transpose.  One key polynomial at a time (64 registers): R0 += D k0 runs over the
-        //      first half of the transpose's loads while k1 arrives, R1 += D k1 over the second half.
-        cplx k0[16], k1[16];
-        const cplx* __restrict__ gk = bk + (size_t)((p > 0 ? p - 1 : 0) * 2) * M + t;
-        if (p > 0) {
-            asm volatile("" : "+l"(gk) :: "memory");                             // not above the stores
-#pragma unroll
-            for (int i = 0; i < 16; i++) k0[i] = __ldg(gk + i * T);
-        }
-        lanes_sync<T>(bar_id);
-        const int b = t / P::P, pp = t % P::P;
-        if (p > 0) {
-            // ---- transpose read, with the previous polynomial's multiply-accumulates between the loads
-            tmem_wait_st();
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    if (h == 0 && c == 2) {                  // half of k0 has been consumed: room for k1
-#pragma unroll
-                        for (int i = 0; i < 16; i++) k1[i] = __ldg(gk + M + i * T);
-                    }
-                    uint32_t d[16], r[16];
-                    TFHE_TLD16(d, tspec + 16 * c); TFHE_TLD16(r, tacc + 64 * h + 16 * c);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const cplx D = unpack_cplx(d, i);
-                        cplx R = unpack_cplx(r, i);
-                        cfma(R, D, h == 0 ? k0[4 * c + i] : k1[4 * c + i]);
-                        pack_cplx(r, i, R);
-                    }
-                    TFHE_TST16(r, tacc + 64 * h + 16 * c);
-#pragma unroll
-                    for (int i = 0; i < 2; i++) v[8 * h + 2 * c + i] = buf[b * P::S + pp + P::P * (8 * h + 2 * c + i)];
-                }
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < 16; u++) v[u] = buf[b * P::S + pp + P::P * u];
-        }
-        Tw8Regs qtw; tw8_issue(qtw, ttw);                        // depths 4-7 twiddles
-        lanes_sync<T>(bar_id);                                   // every lane is done with buf
-        // ---- depths 4-7, exchange, depth 8
-        tree_forward_b_tm(v, qtw);
-        if (p == last) {
-            const cplx* __restrict__ g = bk + (size_t)(p * 2) * M + t;
-            asm volatile("" : "+l"(g) : "d"(v[0].x), "d"(v[1].y), "d"(v[2].x), "d"(v[3].y), "d"(v[4].x), "d"(v[5].y), "d"(v[6].x), "d"(v[7].y),
-                                       "d"(v[8].x), "d"(v[9].y), "d"(v[10].x), "d"(v[11].y), "d"(v[12].x), "d"(v[13].y), "d"(v[14].x), "d"(v[15].y));   // behind the pass
-#pragma unroll
-            for (int i = 0; i < 16; i++) k1[i] = __ldg(g + M + i * T);
-#pragma unroll
-            for (int i = 0; i < 16; i++) k0[i] = __ldg(g + i * T);
-        }
-        tree_forward_c<LOGM, true, true>(v, tw, t, ttw);
-        if (p < last) {
-            // ---- park the spectrum
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                uint32_t d[16];
-#pragma unroll
-                for (int i = 0; i < 4; i++) pack_cplx(d, i, v[4 * c + i]);
-                TFHE_TST16(d, tspec + 16 * c);
-            }
-        } else {
-            mac_tmem<false>(tacc, v, [&](int i) { return k0[i]; });
-            mac_tmem<false>(tacc + 64, v, [&](int i) { return k1[i]; });
-        }
-    }
-    {
-        cplx R0[16], R1[16];
-        load_tmem2(R0, R1, tacc);
-        tree_backward2<LOGM, true, true>(R0, R1, buf, tw, t, bar_id, ttw);
-#pragma unroll
-        for (int m = 0; m < 16; m++) {
-            const int j = t + T * m;
-            acc[j] = (Torus)((PLAIN ? (U)0 : (U)acc[j]) + (U)to_torus(R0[m].x, (Torus)0));
-            acc[j + M] = (Torus)((PLAIN ? (U)0 : (U)acc[j + M]) + (U)to_torus(R0[m].y, (Torus)0));
-            acc[N + j] = (Torus)((PLAIN ? (U)0 : (U)acc[N + j]) + (U)to_torus(R1[m].x, (Torus)0));
-            acc[N + j + M] = (Torus)((PLAIN ? (U)0 : (U)acc[N + j + M]) + (U)to_torus(R1[m].y, (Torus)0));
-        }
-    }
-    lanes_sync<T>(bar_id);      // accumulator writes visible before the next step's rotated reads
-}
-
 // Shared memory: twiddles | CTA control (KeyPipeShared, TMEM base) | key staging (KeyPipe only) | per group: transpose buffer, ACC
 // Tensor memory : per warp R0 (64 columns) | R1 (64) | stash (STASH only), warps of a lane quarter side by side; the key columns
 //                 of the KeyPipe configuration come after the last warp's window.
@@ -898,9 +732,8 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_base_slot;
-    // deferred variant (F2 == 5): per warp R0 | R1 | stash | parked spectrum = 224 columns, the twiddles once per lane quarter at 448
-    const uint32_t tacc = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)(F2 == 5 ? 224 : S::TMEM_COLS);   // R0 | R1 | stash
-    const uint32_t ttw = F2 == 5 ? tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + 448u : (S::TWT ? tacc + (uint32_t)S::TW_COL : 0u);
+    const uint32_t tacc = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)S::TMEM_COLS;   // R0 | R1 | stash
+    const uint32_t ttw = S::TWT ? tacc + (uint32_t)S::TW_COL : 0u;
     if (S::TWT) tree_twiddles_to_tmem<LOGM, S::TT9 || LOGM == 9>(tw, t, ttw);
     KeyPipe kp{kps, smem_raw + S::TW_BYTES + S::CTRL_BYTES, reinterpret_cast<const unsigned char*>(A.bkfft),
                tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)S::KEY_COL, tmem_base + (uint32_t)S::KEY_COL,
@@ -948,8 +781,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
                 if (KM == KM_TMEM) for (int p = 0; p < 2 * l; p++) { kp.acquire(t & 31); kp.release(t & 31); }     // stay aligned with the key stream
                 continue;
             }
-            if constexpr (F2 == 5) cmux_step_deferred<LOGM, Torus>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, tw, t, bar_id, ttw);
-            else if constexpr (F2 == 9) cmux_step_mock<LOGM>(l, A.Bgbit, buf, tacc, tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (GROUPS == 4 ? 224u : 448u),
+            if constexpr (F2 == 9) cmux_step_mock<LOGM>(l, A.Bgbit, buf, tacc, tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (GROUPS == 4 ? 224u : 448u),
                                                         GROUPS == 4 ? 64u : 0u, tw, t, bar_id, ttw);
             else if constexpr (F2 > 0) cmux_step2<LOGM, Torus, F2>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, tw, t, bar_id, ttw);
             else cmux_step<LOGM, Torus, STASH, KM>(acc, a, A.bkfft + (size_t)i * bk_stride, l, A.Bgbit, buf, tacc, kp, tw, t, bar_id, ttw);
@@ -1070,7 +902,6 @@ cudaError_t blind_rotate_init() {
     if ((e = br_attr<10, int64_t, G64, true, KM_REGS2>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, 4, true, KM_REGS2, 9>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32, true, KM_REGS2, 9>()) != cudaSuccess) return e;
-    if ((e = br_attr<9, int32_t, G32, true, KM_REGS2, 5>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32, true, KM_REGS2, 2>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32, true, KM_REGS2, 3>()) != cudaSuccess) return e;
     if ((e = br_attr<10, int64_t, G64, true, KM_REGS2, 3>()) != cudaSuccess) return e;
@@ -1091,7 +922,8 @@ cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
     // key latency in the multiply-accumulate gives back (long_scoreboard 1.4 -> 7.6 %), and 255 registers leave a few spills.
     if (variant && variant[0] == 'm') return br_launch<9, int32_t, 4, true, KM_REGS2, 9>(a, a.count, s);           // ceiling probe, 4 warps per SM
     if (variant && variant[0] == 'M') return br_launch<9, int32_t, G32, true, KM_REGS2, 9>(a, a.count, s);         // ceiling probe, 8 warps per SM
-    if (variant && variant[0] == 'd') return br_launch<9, int32_t, G32, true, KM_REGS2, 5>(a, a.count, s);         // deferred multiply-accumulates
+    // (a variant that deferred the multiply-accumulates of polynomial p into the transpose of p+1 -- spectrum parked in tensor memory --
+    //  was correct and 22 % slower: profiles/r2_notes.md, commit "Experiment (negative): multiply-accumulates ... deferred")
     if (variant && variant[0] == '2') return br_launch<9, int32_t, G32, true, KM_REGS2, 2>(a, a.count, s);
     if (variant && variant[0] == '3') return br_launch<9, int32_t, G32, true, KM_REGS2, 3>(a, a.count, s);
     return br_launch<9, int32_t, G32, true, KM_REGS2>(a, a.count, s);

@@ -15,14 +15,16 @@
 // One CTA = 128 samples (the M dimension = the 128 lanes of tensor memory) x 128 output columns, four s32 accumulator tiles of
 // 128 columns (one per key byte) = all 512 columns of tensor memory.  A STEP covers 32 rows of the one-hot matrix = 32 / base
 // consecutive (i, j) blocks (a group of `base` rows per block: base-1 candidates and one padding row that no digit selects).
-//   warps 0-3  : sample s = thread: read a_i, cut the digits, write the step's 32-byte one-hot row into the A ring (K-major, no swizzle);
-//                at the end read the four tiles back, recombine, negate, add b, store
-//   warp 4     : one thread issues the four MMAs of a step (same A, the four byte planes of the key as B) and commits them to the
-//                slot's `free` barrier
-//   warp 5     : one thread streams the key: one 16 KB bulk copy (TMA) per step into the B ring
-// Key image in global memory: [column group][step][plane][4096 B], every 4 KB block already in the shared-memory image the MMA wants
-//   byte (n, k) at (k / 16) * 2048 + (n / 8) * 128 + (n % 8) * 16 + k % 16        (n = column in the group, k = row of the step)
-// i.e. 8 x 16-byte core matrices, LBO (K direction) 2048, SBO (column direction) 128 -- verified by tools/imma_probe.cu.
+//   producer warps (4 per group, TC_GROUPS groups taking turns step by step): thread = sample: read a_i, cut the digits, write the step's
+//                32-byte one-hot row into the A ring (K-major, no swizzle); at the end read the four tiles back, recombine, negate, add b,
+//                store (each group its share of the columns)
+//   MMA warp   : one thread issues the two MMAs of a step (same A, the two plane pairs of the key as B) and commits them to the slot's
+//                `free` barrier
+//   TMA warp   : one thread streams the key: one 16 KB bulk copy per step into the B ring
+// Key image in global memory: [column group][step][plane pair][8192 B], every 8 KB block already in the shared-memory image the MMA wants:
+// 256 rows (byte plane 2h of the 128 columns, then byte plane 2h+1) x 32 key rows of the step, K-major,
+//   byte (row r, k) at (k / 16) * 4096 + (r / 8) * 128 + (r % 8) * 16 + k % 16
+// i.e. 8 x 16-byte core matrices, LBO (K direction) 4096, SBO (row direction) 128 -- layouts verified by tools/imma_probe.cu.
 #include "engine.h"
 #include "bk_pipe.cuh"
 #include <type_traits>
@@ -30,17 +32,40 @@
 
 namespace tfhe_b200 {
 
-constexpr int TC_STAGES = 8;              // ring depth (steps)
-constexpr int TC_B_BYTES = 16384;         // key bytes per step: 4 planes x 4 KB
+#ifndef TC_STAGES_DEF
+#define TC_STAGES_DEF 8
+#endif
+constexpr int TC_STAGES = TC_STAGES_DEF;  // ring depth (steps)
+constexpr int TC_B_BYTES = 16384;         // key bytes per step: 2 plane pairs x 8 KB
 constexpr int TC_A_BYTES = 4096;          // one-hot image per step: 128 samples x 32 B
-constexpr int TC_THREADS = 192;
-constexpr size_t TC_SMEM = (size_t)TC_STAGES * (TC_B_BYTES + TC_A_BYTES) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+#ifndef TC_GROUPS_DEF
+#define TC_GROUPS_DEF 2
+#endif
+constexpr int TC_GROUPS = TC_GROUPS_DEF;  // producer warp sets taking turns step by step (1, 2 or 4)
+constexpr int TC_THREADS = 128 * TC_GROUPS + 64;        // 4 producer / epilogue warps per group, the MMA warp, the TMA warp
+#ifndef TC_PF_DEF
+#define TC_PF_DEF 4
+#endif
+constexpr int TC_PF = TC_PF_DEF;          // input coefficients requested ahead of their use, per sample
+#ifndef TC_CLUSTER_DEF
+#define TC_CLUSTER_DEF 1
+#endif
+// CTAs per cluster (1 or 2).  2: two sample tiles of the same column group form a cluster and share ONE key stream -- each CTA fetches half
+// of every step's 16 KB and multicasts it into both shared memories (TMA .multicast::cluster), the step's MMA commit releases the slot in
+// both CTAs -- so the L2 -> SM traffic of the key halves.
+constexpr int TC_CLUSTER = TC_CLUSTER_DEF;
+constexpr size_t TC_SMEM_BASE = (size_t)TC_STAGES * (TC_B_BYTES + TC_A_BYTES) + 1024 /*alignment slack*/ + 512 /*barriers*/;
+constexpr size_t TC_SMEM = TC_SMEM_BASE + (size_t)4 * TC_GROUPS * 32 * 33 * 4;     // + the producers' input tiles
 
-__host__ __device__ inline uint64_t tc_desc(uint32_t saddr) {          // K-major, no swizzle, LBO 2048 / SBO 128, sm_100 descriptor version
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+// K-major, no swizzle, sm_100 descriptor version; lbo = distance between the two 16-byte K chunks (rows * 16), SBO = 128 (8-row groups)
+__host__ __device__ inline uint64_t tc_desc(uint32_t saddr, uint32_t lbo) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
 }
+// One MMA covers TWO byte planes: the B tile is 256 rows (plane 2h in rows 0-127, plane 2h+1 in rows 128-255), N = 256.  An i8 MMA
+// costs ~76 cycles + 0.66 cycles per column of N (tools/imma_probe.cu: 161 cycles at N = 128, 246 at N = 256), so two wide MMAs per step
+// (492 cycles) beat four narrow ones (646).
 // cute::UMMA::InstrDescriptor: c_format[4,6)=2 (s32), a/b_format = 0 (u8), a/b_major = 0 (K), n_dim[17,23) = N>>3, m_dim[24,29) = M>>4
-constexpr uint32_t TC_IDESC = (2u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t TC_IDESC = (2u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -50,6 +75,18 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t mask) {      // arrives on `bar` (same offset) in every CTA of the mask
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) {} }
 #define TC_TLD16(r, addr)                                                                                                      \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"       \
@@ -57,8 +94,11 @@ __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity) { while 
                    "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                     \
                  : "r"(addr) : "memory")
 
+#ifndef TC_DBG
+#define TC_DBG 0              // development ablations (wrong results): 1 = no MMAs, 2 = no key copies, 4 = no digit work, 8 = no input loads
+#endif
 template <typename TorusIn, int BASEBIT>
-__global__ void __launch_bounds__(TC_THREADS, 1) keyswitch_tc_kernel(const KSArgs A) {
+__global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS, 1) keyswitch_tc_kernel(const KSArgs A) {
     typedef typename std::conditional<sizeof(TorusIn) == 4, uint32_t, uint64_t>::type U;
     constexpr int W = sizeof(TorusIn) * 8;
     constexpr int BASE = 1 << BASEBIT;
@@ -69,10 +109,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) keyswitch_tc_kernel(const KSArg
     unsigned char* ringA = smem + (size_t)TC_STAGES * TC_B_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ringA + (size_t)TC_STAGES * TC_A_BYTES);
     uint64_t* full = bars;                       // key bytes of the step have landed (TMA, byte count)
-    uint64_t* ready = bars + TC_STAGES;          // the four producer warps have written the step's one-hot rows
+    uint64_t* ready = bars + TC_STAGES;          // the four producer warps whose turn it is have written the step's one-hot rows
     uint64_t* freeb = bars + 2 * TC_STAGES;      // the step's MMAs have completed: both ring slots may be overwritten
     uint64_t* done = bars + 3 * TC_STAGES;       // all MMAs have completed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 1);
+    unsigned char* tiles = reinterpret_cast<unsigned char*>(bars) + 512;       // per producer warp: 32 samples x 32 coefficients (+1 pad) x 4 B
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = A.rows_in * A.t;
@@ -81,7 +122,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) keyswitch_tc_kernel(const KSArg
                                    (size_t)blockIdx.y * nsteps * TC_B_BYTES;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(full + s, 1); mbar_init(ready + s, 4); mbar_init(freeb + s, 1); }
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(full + s, 1); mbar_init(ready + s, 4); mbar_init(freeb + s, TC_CLUSTER); }
         mbar_init(done, 1);
         mbar_fence_init();
     }
@@ -91,20 +132,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) keyswitch_tc_kernel(const KSArg
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (TC_CLUSTER > 1) cluster_sync_all();              // the peer's barriers exist before anything is multicast at them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
+    const uint32_t crank = TC_CLUSTER > 1 ? cluster_ctarank() : 0u;
 
-    if (warp == 5) {
+    if (warp == 4 * TC_GROUPS + 1) {
         // ---- key stream
         if (lane == 0) {
             for (int st = 0; st < nsteps; st++) {
                 const int slot = st % TC_STAGES, use = st / TC_STAGES;
                 if (use > 0) tc_wait(freeb + slot, (uint32_t)(use - 1) & 1u);
+                if (TC_DBG & 2) { mbar_arrive(full + slot); continue; }
                 mbar_expect_tx(full + slot, TC_B_BYTES);
+                if (TC_CLUSTER > 1) {
+                    constexpr uint32_t PART = TC_B_BYTES / TC_CLUSTER;
+                    tma_load_1d_multicast(ringB + (size_t)slot * TC_B_BYTES + crank * PART, kstream + (size_t)st * TC_B_BYTES + crank * PART, PART,
+                                          full + slot, (uint16_t)((1u << TC_CLUSTER) - 1u));
+                } else
                 tma_load_1d(ringB + (size_t)slot * TC_B_BYTES, kstream + (size_t)st * TC_B_BYTES, TC_B_BYTES, full + slot);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 4 * TC_GROUPS) {
         // ---- MMA issue
         if (lane == 0) {
             for (int st = 0; st < nsteps; st++) {
@@ -112,36 +161,101 @@ __global__ void __launch_bounds__(TC_THREADS, 1) keyswitch_tc_kernel(const KSArg
                 tc_wait(full + slot, ph);
                 tc_wait(ready + slot, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t da = tc_desc(smem_u32(ringA + (size_t)slot * TC_A_BYTES));
+                const uint64_t da = tc_desc(smem_u32(ringA + (size_t)slot * TC_A_BYTES), 2048);
                 const uint32_t sb = smem_u32(ringB + (size_t)slot * TC_B_BYTES);
 #pragma unroll
-                for (int p = 0; p < 4; p++) tc_mma_i8(tmem + 128u * p, da, tc_desc(sb + 4096u * p), st > 0 ? 1u : 0u);
-                tc_commit(freeb + slot);
+                for (int h = 0; h < 2; h++) if (!(TC_DBG & 1)) tc_mma_i8(tmem + 256u * h, da, tc_desc(sb + 8192u * h, 4096), st > 0 ? 1u : 0u);
+                if (TC_CLUSTER > 1) tc_commit_multicast(freeb + slot, (uint16_t)((1u << TC_CLUSTER) - 1u));
+                else tc_commit(freeb + slot);
             }
             tc_commit(done);
         }
     } else {
-        // ---- one-hot rows: thread = sample
-        const int m = threadIdx.x;
+        // ---- one-hot rows: TC_GROUPS threads per sample, thread (m, g) builds the rows of sample m for the steps st = g (mod TC_GROUPS).
+        //      What a producer warp spends per step is not arithmetic but a chain of small latencies (slot wait, branches on the block
+        //      counters, store, proxy fence, warp sync, arrive): ~900 cycles per step measured -- with one warp set doing every step that
+        //      chain, not the tensor core (492 cycles per step), set the pace, and splitting each ROW between two threads changed nothing
+        //      (profiles/r2_notes.md).  Taking turns step by step gives every warp TC_GROUPS step times per row.
+        const int m = threadIdx.x & 127, g = threadIdx.x >> 7;
         const long smp = (long)blockIdx.x * 128 + m;
         const bool live = smp < A.count;
         const TorusIn* in = reinterpret_cast<const TorusIn*>(A.in) + (size_t)(live ? smp : 0) * A.in_stride;
         const U prec_offset = (U)1 << (W - (1 + BASEBIT * A.t));      // cb/lwe_functions.cpp:141 ; poc:444,674
         const uint32_t row_off = (uint32_t)(m >> 3) * 128u + (uint32_t)(m & 7) * 16u;
-        // digits of coefficient i live in the top 32 bits of a_i + prec_offset; the value for the NEXT coefficient is requested one
-        // coefficient ahead so its latency hides behind a whole coefficient's worth of steps
-        int i_cur = 0, j_cur = 0;
-        uint32_t a_cur = live ? (uint32_t)(((U)in[0] + prec_offset) >> (W - 32)) : 0u;
-        U raw_next = (live && A.rows_in > 1) ? (U)in[1] : (U)0;
-        for (int st = 0; st < nsteps; st++) {
+        // The digits of a sample form one BIT STREAM: coefficient i contributes its top t * basebit bits (of a_i + prec_offset), digit 0
+        // first, and a step consumes the next Q * basebit bits of it.  The stream runs through a 64-bit buffer (valid bits at the top),
+        // refilled one coefficient at a time, so a step's digits come out by constant shifts -- no per-block counters and branches
+        // (those, ~25 cycles of branch latency per block, were what bounded the base-4 instances: 8 blocks per step).
+        // Input: a thread walking its own sample row touches one 32-byte sector per load and 32 different lines per warp instruction --
+        // with a new coefficient every step those loads alone cost a third of the gate key switch (ablation in profiles/r2_notes.md).
+        // There each warp reads its 32 samples in tiles of 32 coefficients with lane = coefficient (one coalesced row segment per
+        // instruction), keeps the top 32 bits of a + prec_offset, and transposes the tile through shared memory; the next tile waits in
+        // registers while the current one is used.
+        const int cbits = BASEBIT * A.t;                              // bits per coefficient
+        constexpr int SBITS = Q * BASEBIT;                            // bits per step
+        int i_next = 0;                                               // next coefficient to enter the buffer
+        uint64_t bitbuf = 0; int nbits = 0;
+        // TILED input (32-bit torus: one new coefficient per step at t = 8) or a per-thread register queue TC_PF coefficients deep
+        // (64-bit torus, a new coefficient every 2.5 steps: the strided loads are no burden there and the queue measured faster)
+        constexpr bool TILED = sizeof(TorusIn) == 4;
+        uint32_t* tile = reinterpret_cast<uint32_t*>(tiles) + (size_t)warp * (32 * 33);
+        const long s0w = (long)blockIdx.x * 128 + (m & ~31);         // first sample of this warp
+        const TorusIn* inw = reinterpret_cast<const TorusIn*>(A.in);
+        uint32_t nxt[TILED ? 32 : 1];                                 // next tile: coefficient 32 c + lane of the warp's 32 samples
+        U raw_q[TILED ? 1 : TC_PF];
+        auto fetch_tile = [&](int c) {
+            const int i = 32 * c + lane;
+#pragma unroll
+            for (int r = 0; r < (TILED ? 32 : 1); r++) {
+                U v = (U)0;
+                if (!(TC_DBG & 8) && s0w + r < A.count && i < A.rows_in) v = (U)inw[(size_t)(s0w + r) * A.in_stride + i];
+                nxt[r] = (uint32_t)((v + prec_offset) >> (W - 32));
+            }
+        };
+        auto store_tile = [&]() {
+            __syncwarp();                                             // everybody has read the old tile
+#pragma unroll
+            for (int r = 0; r < (TILED ? 32 : 1); r++) tile[r * 33 + lane] = nxt[r];
+            __syncwarp();
+        };
+        if constexpr (TILED) { fetch_tile(0); store_tile(); fetch_tile(1); }
+        else {
+#pragma unroll
+            for (int x = 0; x < TC_PF; x++) raw_q[x] = (!(TC_DBG & 8) && live && x < A.rows_in) ? (U)in[x] : (U)0;
+        }
+        auto refill = [&]() {
+            uint32_t a32 = 0u;                                        // past the last coefficient: zero digits (the tail of the last step)
+            if constexpr (TILED) {
+                if (i_next && (i_next & 31) == 0) { store_tile(); fetch_tile((i_next >> 5) + 1); }       // (warp-uniform: all lanes refill together)
+                if (live && i_next < A.rows_in) a32 = tile[(m & 31) * 33 + (i_next & 31)];
+            } else {
+                if (live && i_next < A.rows_in) a32 = (uint32_t)((raw_q[0] + prec_offset) >> (W - 32));
+#pragma unroll
+                for (int x = 0; x + 1 < TC_PF; x++) raw_q[x] = raw_q[x + 1];
+                raw_q[TC_PF - 1] = (!(TC_DBG & 8) && live && i_next + TC_PF < A.rows_in) ? (U)in[i_next + TC_PF] : (U)0;
+            }
+            i_next++;
+            bitbuf |= (uint64_t)(a32 >> (32 - cbits)) << (64 - nbits - cbits);
+            nbits += cbits;
+        };
+        auto drop = [&](int n) {                                      // skip n bits of the stream (the other groups' steps)
+            while (n > 0) {
+                if (nbits == 0) refill();
+                const int k = n < nbits ? n : nbits;
+                bitbuf <<= k; nbits -= k; n -= k;
+            }
+        };
+        drop(g * SBITS);                                              // group g starts at step g
+        for (int st = g; st < nsteps; st += TC_GROUPS) {
             const int slot = st % TC_STAGES, use = st / TC_STAGES;
+            if (!(TC_DBG & 4)) { while (nbits < SBITS) refill(); }
             uint32_t w[8];
 #pragma unroll
             for (int x = 0; x < 8; x++) w[x] = 0u;
+            const uint32_t top = (uint32_t)(bitbuf >> 32);            // SBITS <= 16: the step's digits sit in the top word
 #pragma unroll
             for (int q = 0; q < Q; q++) {
-                uint32_t d = (a_cur >> (32 - (j_cur + 1) * BASEBIT)) & (uint32_t)(BASE - 1);
-                if (i_cur >= A.rows_in) d = 0u;                     // tail of the last step
+                const uint32_t d = (top >> (32 - (q + 1) * BASEBIT)) & (uint32_t)(BASE - 1);
                 // one-hot byte d-1 of this block's group of BASE bytes (nothing for d = 0)
                 if constexpr (BASE == 4) w[q] = (1u << (8 * d)) >> 8;
                 else if constexpr (BASE == 8) {
@@ -150,12 +264,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) keyswitch_tc_kernel(const KSArg
                 } else {                                            // BASE == 2: two bytes per block, candidate byte first
                     w[q >> 1] |= d << (16 * (q & 1));
                 }
-                if (++j_cur == A.t) {                               // next coefficient
-                    j_cur = 0; i_cur++;
-                    a_cur = live ? (uint32_t)((raw_next + prec_offset) >> (W - 32)) : 0u;
-                    if (live && i_cur + 1 < A.rows_in) raw_next = (U)in[i_cur + 1];
-                }
             }
+            bitbuf <<= SBITS; nbits -= SBITS;
+            if (!(TC_DBG & 4)) drop((TC_GROUPS - 1) * SBITS);
             if (use > 0) tc_wait(freeb + slot, (uint32_t)(use - 1) & 1u);
             unsigned char* arow = ringA + (size_t)slot * TC_A_BYTES + row_off;
             *reinterpret_cast<uint4*>(arow) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -167,12 +278,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) keyswitch_tc_kernel(const KSArg
         // ---- epilogue: D[sample][column] of byte plane p sits in lane = sample, column 128 p + column
         tc_wait(done, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tl = tmem + (((uint32_t)warp * 32u) << 16);
+        const uint32_t tl = tmem + (((uint32_t)(warp & 3) * 32u) << 16);        // warps w and w + 4 reach the same lane quarter
         int32_t* orow = nullptr;
         if (live) orow = A.out + (size_t)blockIdx.z * A.out_z_stride + (size_t)(smp / A.group) * A.out_stride + (size_t)(smp % A.group) * A.out_inner;
         const int colbase = blockIdx.y * 128;
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 16) {
+        for (int c = (128 / TC_GROUPS) * g; c < (128 / TC_GROUPS) * (g + 1); c += 16) {       // each of the sample's threads stores its share of the columns
             uint32_t p0[16], p1[16], p2[16], p3[16];
             TC_TLD16(p0, tl + c); TC_TLD16(p1, tl + 128 + c); TC_TLD16(p2, tl + 256 + c); TC_TLD16(p3, tl + 384 + c);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -192,6 +303,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) keyswitch_tc_kernel(const KSArg
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    if (TC_CLUSTER > 1) cluster_sync_all();              // nobody leaves while the peer may still signal its barriers
 }
 
 template <typename TorusIn, int BASEBIT>
@@ -202,7 +314,7 @@ static cudaError_t launch_ks_tc_b(const KSArgs& a, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         attr_done.done();
     }
-    dim3 grid((a.count + 127) / 128, a.cols_pad / 128, a.nz > 0 ? a.nz : 1);
+    dim3 grid(((a.count + 127) / 128 + TC_CLUSTER - 1) / TC_CLUSTER * TC_CLUSTER, a.cols_pad / 128, a.nz > 0 ? a.nz : 1);
     keyswitch_tc_kernel<TorusIn, BASEBIT><<<grid, TC_THREADS, TC_SMEM, s>>>(a);
     return cudaGetLastError();
 }
@@ -238,9 +350,10 @@ __global__ void ks_tc_repack_kernel(unsigned char* __restrict__ dst, const int32
         const size_t step = blk / Q; const int q = (int)(blk % Q);
         const int k = q * base + d - 1;
         const int n = c & 127; const size_t cg = (size_t)c >> 7;
-        const size_t off = (size_t)(k >> 4) * 2048 + (size_t)(n >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 15);
+        // byte plane pl of column n = row (pl & 1) * 128 + n of pair tile pl >> 1; a pair tile is [K chunk 2][row group 32][8 rows][16 B]
+        const size_t off = (size_t)(k >> 4) * 4096 + (size_t)(n >> 3) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 15);
         unsigned char* img = dst + (cg * nsteps + step) * (size_t)TC_B_BYTES + off;
-        img[0] = (unsigned char)v; img[4096] = (unsigned char)(v >> 8); img[8192] = (unsigned char)(v >> 16); img[12288] = (unsigned char)(v >> 24);
+        img[0] = (unsigned char)v; img[2048] = (unsigned char)(v >> 8); img[8192] = (unsigned char)(v >> 16); img[8192 + 2048] = (unsigned char)(v >> 24);
     }
 }
 

@@ -16,13 +16,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
                    "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                      \
                  : "r"(addr) : "memory")
 
-__host__ __device__ inline uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+__host__ __device__ inline uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout = 0) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;          // descriptor version (sm_100)
-    return d;                        // layout type (bits 61..63) = 0: no swizzle
+    d |= (uint64_t)(layout & 7) << 61;   // 0: no swizzle, 6: SWIZZLE_32B
+    return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format [4,6) = 2 (s32), a_format [7,10) = 0 (u8), b_format [10,13) = 0 (u8),
 // a_major bit 15 = 0 (K), b_major bit 16 = 0 (K), n_dim [17,23) = N >> 3, m_dim [24,29) = M >> 4
@@ -49,21 +50,26 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
 __host__ __device__ inline int a_val(int m, int k) { return (m * 7 + k * 3 + (m >> 3)) % 5; }
 __host__ __device__ inline int b_val(int n, int k) { return (n * 5 + k * 11 + (n >> 2)) % 7; }
 
-// layout mode 0: image [kchunk][rowgroup][8 rows][16 B]  -> K-chunk stride 2048, row-group stride 128
-__global__ void __launch_bounds__(128) probe(int32_t* out, long long* cyc, int lbo, int sbo, int nrep) {
+// mode bit 0: N = 256 per MMA (two byte planes side by side as 256 B rows), 2 MMAs per step instead of 4
+// mode bit 1: SWIZZLE_32B operand layout (rows of 32 contiguous bytes, 8-row groups 256 B apart, 16-byte halves swapped in rows 4-7)
+// no swizzle: image [kchunk][rowgroup][8 rows][16 B]  -> K-chunk stride rows*16, row-group stride 128
+__device__ __host__ inline int img_off(int r, int k, int rows, int swz) {
+    if (!swz) return (k / 16) * (rows * 16) + (r / 8) * 128 + (r % 8) * 16 + (k % 16);
+    const int chunk = (k / 16) ^ ((r >> 2) & 1);
+    return (r / 8) * 256 + (r % 8) * 32 + chunk * 16 + (k % 16);
+}
+__global__ void __launch_bounds__(128) probe(int32_t* out, long long* cyc, int mode, int nrep) {
     __shared__ uint32_t tbase_s;
     __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(8) uint64_t ring[4];
-    extern __shared__ __align__(1024) unsigned char sm[];
+    extern __shared__ __align__(1024) unsigned char sm_raw[];
+    unsigned char* sm = (unsigned char*)(((uintptr_t)sm_raw + 1023) & ~(uintptr_t)1023);
+    const int NB = (mode & 1) ? 256 : 128, swz = (mode >> 1) & 1;
     unsigned char* A = sm;
     unsigned char* B = sm + 4096;
     const int w = threadIdx.x >> 5;
-    for (int e = threadIdx.x; e < 128 * 32; e += 128) {
-        const int r = e / 32, k = e % 32;
-        const int off = (k / 16) * 2048 + (r / 8) * 128 + (r % 8) * 16 + (k % 16);
-        A[off] = (unsigned char)a_val(r, k);
-        B[off] = (unsigned char)b_val(r, k);
-    }
+    for (int e = threadIdx.x; e < 128 * 32; e += 128) { const int r = e / 32, k = e % 32; A[img_off(r, k, 128, swz)] = (unsigned char)a_val(r, k); }
+    for (int e = threadIdx.x; e < NB * 32; e += 128) { const int r = e / 32, k = e % 32; B[img_off(r, k, NB, swz)] = (unsigned char)b_val(r, k); }
     if (w == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tbase_s)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -78,13 +84,13 @@ __global__ void __launch_bounds__(128) probe(int32_t* out, long long* cyc, int l
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tbase = tbase_s;
-    const uint64_t da = make_desc(smem_u32(A), lbo, sbo), db = make_desc(smem_u32(B), lbo, sbo);
-    const uint32_t idesc = make_idesc(128, 128);
+    const uint64_t da = swz ? make_desc(smem_u32(A), 16, 256, 6) : make_desc(smem_u32(A), 128 * 16, 128);
+    const uint64_t db = swz ? make_desc(smem_u32(B), 16, 256, 6) : make_desc(smem_u32(B), NB * 16, 128);
+    const uint32_t idesc = make_idesc(128, NB);
     uint32_t parity = 0;
     if (threadIdx.x == 0) {
         mma_i8(tbase, da, db, idesc, 0);            // D  = A B^T
         mma_i8(tbase, da, db, idesc, 1);            // D += A B^T
-        mma_i8(tbase + 128, da, db, idesc, 0);      // second accumulator tile, columns 128..255
         commit(&bar);
     }
     wait_bar(&bar, parity); parity ^= 1;
@@ -98,13 +104,13 @@ __global__ void __launch_bounds__(128) probe(int32_t* out, long long* cyc, int l
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    // throughput: nrep steps of 4 MMAs (the four byte planes of a key-switch step), one commit per step, at most 4 steps in flight
+    // throughput: nrep steps covering 512 accumulator columns (4 MMAs of N = 128 or 2 of N = 256), one commit per step
     if (threadIdx.x == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const long long t0 = clock64();
         for (int s = 0; s < nrep; s++) {            // one barrier per step in flight: a barrier must not run more than one phase ahead of its waiter
             if (s >= 4) wait_bar(&ring[s & 3], ((s >> 2) - 1) & 1);
-            for (int p = 0; p < 4; p++) mma_i8(tbase + 128 * p, da, db, idesc, 1);
+            for (int p = 0; p < 512 / NB; p++) mma_i8(tbase + NB * p, da, db, idesc, 1);
             commit(&ring[s & 3]);
         }
         for (int s = nrep - 4 < 0 ? 0 : nrep - 4; s < nrep; s++) wait_bar(&ring[s & 3], (s >> 2) & 1);
@@ -119,27 +125,25 @@ int main() {
     int32_t* out; long long* cyc;
     cudaMalloc(&out, 128 * 256 * 4); cudaMalloc(&cyc, 8);
     int32_t* h = (int32_t*)malloc(128 * 256 * 4);
-    cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384);
-    const int cfg[2][2] = {{2048, 128}, {128, 2048}};       // (LBO, SBO)
-    for (int c = 0; c < 2; c++) {
+    cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
+    const char* names[4] = {"N=128 x4, no swizzle", "N=256 x2, no swizzle", "N=128 x4, SWIZZLE_32B", "N=256 x2, SWIZZLE_32B"};
+    for (int mode = 0; mode < 4; mode++) {
         cudaMemset(out, 0xff, 128 * 256 * 4);
-        probe<<<1, 128, 16384>>>(out, cyc, cfg[c][0], cfg[c][1], 4096);
+        probe<<<1, 128, 32768>>>(out, cyc, mode, 4096);
         cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { printf("LBO=%d SBO=%d: %s\n", cfg[c][0], cfg[c][1], cudaGetErrorString(e)); return 1; }
+        if (e != cudaSuccess) { printf("%s: %s\n", names[mode], cudaGetErrorString(e)); return 1; }
         cudaMemcpy(h, out, 128 * 256 * 4, cudaMemcpyDeviceToHost);
         long long hc; cudaMemcpy(&hc, cyc, 8, cudaMemcpyDeviceToHost);
         int to = 0; cudaMemcpyFromSymbol(&to, g_timeout, 4); if (to) printf("  (a barrier wait timed out)\n");
-        int bad2 = 0, bad1 = 0;
+        const int NB = (mode & 1) ? 256 : 128;
+        int bad = 0;
         for (int m = 0; m < 128; m++)
-            for (int n = 0; n < 128; n++) {
+            for (int n = 0; n < NB; n++) {
                 int ref = 0;
                 for (int k = 0; k < 32; k++) ref += a_val(m, k) * b_val(n, k);
-                if (h[m * 256 + n] != 2 * ref) bad2++;
-                if (h[m * 256 + 128 + n] != ref) bad1++;
+                if (h[m * 256 + n] != 2 * ref) bad++;
             }
-        printf("LBO=%d SBO=%d: accumulated tile mismatches %d, plain tile mismatches %d of 16384; D[0][0..3] = %d %d %d %d (expect x2: %d..)  "
-               "%.1f cycles per 4-MMA step\n", cfg[c][0], cfg[c][1], bad2, bad1, h[0], h[1], h[2], h[3],
-               2 * [] { int r = 0; for (int k = 0; k < 32; k++) r += a_val(0, k) * b_val(0, k); return r; }(), (double)hc / 4096);
+        printf("%-24s mismatches %d of %d;  %.1f cycles per 512-column step\n", names[mode], bad, 128 * NB, (double)hc / 4096);
     }
     return 0;
 }
