@@ -24,6 +24,9 @@
 #include "bk_pipe.cuh"
 #include <cstdlib>
 
+#ifndef BR_SHARE_TW64
+#define BR_SHARE_TW64 0       // 1: Torus64 with stash keeps the per-lane twiddles ONCE per lane quarter, depth 9 included (measured slower: 196 vs 187 ms)
+#endif
 #ifndef BR_FASTDIGIT
 #define BR_FASTDIGIT 1
 #endif
@@ -597,8 +600,11 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
             // (no wait::st here: the reload at the next level waits)
         }
         TL(1);
-        if (p == 0) forward_and_mac<LOGM, true, KM, STASH && sizeof(Torus) == 8>(v, tacc, bk, buf, kp, tw, t, bar_id, ttw);
-        else        forward_and_mac<LOGM, false, KM, STASH && sizeof(Torus) == 8>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp, tw, t, bar_id, ttw);
+        // depth-9 twiddles (N = 2048) come from shared memory only where the Torus64 stash has taken their tensor-memory columns and the
+        // twiddles are not shared per lane quarter
+        constexpr bool NOTT9 = STASH && sizeof(Torus) == 8 && !(BR_SHARE_TW64 && KM == KM_REGS2);
+        if (p == 0) forward_and_mac<LOGM, true, KM, NOTT9>(v, tacc, bk, buf, kp, tw, t, bar_id, ttw);
+        else        forward_and_mac<LOGM, false, KM, NOTT9>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp, tw, t, bar_id, ttw);
     }
     // every lane has finished reading the accumulator once it passes the first sync inside the backward transform
     if constexpr (KM == KM_REGS2) {
@@ -607,7 +613,7 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
         TL(0);
         load_tmem2(R0, R1, tacc);
         TL(9);
-        tree_backward2<LOGM, true, !(STASH && sizeof(Torus) == 8)>(R0, R1, buf, tw, t, bar_id, ttw);
+        tree_backward2<LOGM, true, !(STASH && sizeof(Torus) == 8 && !BR_SHARE_TW64)>(R0, R1, buf, tw, t, bar_id, ttw);
 #pragma unroll
         for (int m = 0; m < 16; m++) {
             const int j = t + T * m;
@@ -669,10 +675,15 @@ template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM> struct BRSme
     static constexpr bool TWT = KM == KM_REGS2;                                         // per-lane twiddles in tensor memory (tree_fft.cuh)
     static constexpr int TW_COL = 128 + (STASH ? 4 * StashWords<Torus>::PER_C : 0);
     // depth-9 twiddles (N = 2048) stay in shared memory when the 64-column stash of Torus64 needs their place
-    static constexpr bool TT9 = TWT && P::NS > 1 && !(STASH && sizeof(Torus) == 8);
-    static constexpr int TMEM_COLS = TW_COL + (TWT ? 32 * (2 + (TT9 ? 1 : 0)) : 0);
+    // SHARE: warps w and w + 4 sit in the same lane quarter and their lanes have the same t, hence the same twiddles -- one copy per
+    // quarter behind the two warps' windows.  Used where the windows are full otherwise (Torus64: R 128 | stash 64, twice, + 96 = 480).
+    static constexpr bool SHARE = BR_SHARE_TW64 && TWT && STASH && sizeof(Torus) == 8 && WARPS == 8;
+    static constexpr bool TT9 = TWT && P::NS > 1 && (!(STASH && sizeof(Torus) == 8) || SHARE);
+    static constexpr int TW_COLS = TWT ? 32 * (2 + (TT9 ? 1 : 0)) : 0;
+    static constexpr int TMEM_COLS = TW_COL + (SHARE ? 0 : TW_COLS);                    // per-warp window
+    static constexpr int SHARED_TW_COL = 2 * TW_COL;                                     // SHARE: the quarter's twiddles
     static constexpr int KEY_COL = (WARPS + 3) / 4 * TMEM_COLS;
-    static_assert(KEY_COL + (KM == KM_TMEM ? 128 : 0) <= 512, "tensor memory columns exceeded");
+    static_assert(KEY_COL + (KM == KM_TMEM ? 128 : 0) + (SHARE ? TW_COLS : 0) <= 512, "tensor memory columns exceeded");
     static_assert(KM != KM_TMEM || P::T == 32, "KeyPipe: one warp per accumulator");
 };
 
@@ -733,7 +744,7 @@ __global__ void __launch_bounds__(GROUPS * TreePlan<LOGM>::T, 1) blind_rotate_ke
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_base_slot;
     const uint32_t tacc = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)S::TMEM_COLS;   // R0 | R1 | stash
-    const uint32_t ttw = S::TWT ? tacc + (uint32_t)S::TW_COL : 0u;
+    const uint32_t ttw = !S::TWT ? 0u : S::SHARE ? tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)S::SHARED_TW_COL : tacc + (uint32_t)S::TW_COL;
     if (S::TWT) tree_twiddles_to_tmem<LOGM, S::TT9 || LOGM == 9>(tw, t, ttw);
     KeyPipe kp{kps, smem_raw + S::TW_BYTES + S::CTRL_BYTES, reinterpret_cast<const unsigned char*>(A.bkfft),
                tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)S::KEY_COL, tmem_base + (uint32_t)S::KEY_COL,
