@@ -72,7 +72,8 @@ typedef struct {
 /* Replaces init_LweBootstrappingKeyFFT (cb/lwe_functions.cpp:287-316): takes the coefficient-domain
  * bootstrapping key bk[n][2l][2][N] and the key-switching key ks[N][t][base][n+1] from HOST memory,
  * transforms bk on the device (tGswToFFTConvert, cb/tgsw_functions.cpp:389-394) into the engine's
- * private spectral layout and repacks ks for coalesced reads. */
+ * private spectral layout and repacks ks on the device: by default into byte-plane images for the tensor-core key switch,
+ * with TFHE_B200_KS=cuda in the environment into rows for the CUDA-core kernels (one choice per process, same results). */
 int tfhe_b200_gate_load_keys(tfhe_b200_ctx* ctx, const tfhe_b200_gate_params* p,
                              const int32_t* bk_host, const int32_t* ks_host);
 /* Multi-GPU replication: rank 0 loads keys, every other rank allocates, then the two
