@@ -18,8 +18,8 @@
 //   producer warps (4 per group, TC_GROUPS groups taking turns step by step): thread = sample: read a_i, cut the digits, write the step's
 //                32-byte one-hot row into the A ring (K-major, no swizzle); at the end read the four tiles back, recombine, negate, add b,
 //                store (each group its share of the columns)
-//   MMA warp   : one thread issues the two MMAs of a step (same A, the two plane pairs of the key as B) and commits them to the slot's
-//                `free` barrier
+//   MMA warps  : TC_MMAW issuing threads taking turns step by step: the two MMAs of a step (same A, the two plane pairs of the key as B),
+//                committed to the slot's `free` barrier
 //   TMA warp   : one thread streams the key: one 16 KB bulk copy per step into the B ring
 // Key image in global memory: [column group][step][plane pair][8192 B], every 8 KB block already in the shared-memory image the MMA wants:
 // 256 rows (byte plane 2h of the 128 columns, then byte plane 2h+1) x 32 key rows of the step, K-major,
@@ -42,11 +42,24 @@ constexpr int TC_A_BYTES = 4096;          // one-hot image per step: 128 samples
 #define TC_GROUPS_DEF 2
 #endif
 constexpr int TC_GROUPS = TC_GROUPS_DEF;  // producer warp sets taking turns step by step (1, 2 or 4)
-constexpr int TC_THREADS = 128 * TC_GROUPS + 64;        // 4 producer / epilogue warps per group, the MMA warp, the TMA warp
-#ifndef TC_PF_DEF
-#define TC_PF_DEF 4
+#ifndef TC_MMAW_DEF
+#define TC_MMAW_DEF 2
 #endif
-constexpr int TC_PF = TC_PF_DEF;          // input coefficients requested ahead of their use, per sample
+// MMA-issuing warps taking turns step by step.  tcgen05.commit holds its issuing thread for ~370 cycles, during which the thread queues
+// nothing and the tensor pipe runs dry: one issuer committing every step gets 544 cycles per step, two get 272, three reach the pipe's
+// 256 (tools/imma_probe.cu, profiles/r2_imma_probe3.txt).  A commit covers the committing thread's MMAs only, so each slot is still
+// released by the thread that consumed it; the integer accumulation does not care in which order the tensor core takes the streams
+// (the accumulators are zeroed up front instead of relying on a first non-accumulating MMA).
+constexpr int TC_MMAW = TC_MMAW_DEF;
+#ifndef TC_SPT_DEF
+#define TC_SPT_DEF 4
+#endif
+constexpr int TC_SPT = TC_SPT_DEF;        // consecutive steps a producer group writes per turn
+// A ring slot must always be served by the SAME producer group and the SAME issuing warp: each of them walks its own steps in order, so
+// it is never more than one phase ahead of a slot's mbarriers.  (With 3 issuers on 8 slots an issuer could poll a barrier two uses
+// ahead, where the parity test aliases -- measured as sporadic launch failures.)
+static_assert(TC_STAGES % (TC_GROUPS * TC_SPT) == 0 && TC_STAGES % TC_MMAW == 0, "ring slots must map to fixed producer groups / MMA issuers");
+constexpr int TC_THREADS = 128 * TC_GROUPS + 32 * TC_MMAW + 32;        // 4 producer / epilogue warps per group, the MMA warps, the TMA warp
 #ifndef TC_CLUSTER_DEF
 #define TC_CLUSTER_DEF 1
 #endif
@@ -123,7 +136,7 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(full + s, 1); mbar_init(ready + s, 4); mbar_init(freeb + s, TC_CLUSTER); }
-        mbar_init(done, 1);
+        mbar_init(done, TC_MMAW);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -136,8 +149,23 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     const uint32_t crank = TC_CLUSTER > 1 ? cluster_ctarank() : 0u;
+    if (warp < 4) {                                       // zero the four accumulator tiles (every MMA accumulates)
+        uint32_t z[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) z[i] = 0u;
+        const uint32_t tq = tmem + (((uint32_t)warp * 32u) << 16);
+#pragma unroll 1
+        for (int c = 0; c < 512; c += 16)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"
+                         ::"r"(z[0]), "r"(z[1]), "r"(z[2]), "r"(z[3]), "r"(z[4]), "r"(z[5]), "r"(z[6]), "r"(z[7]), "r"(z[8]), "r"(z[9]),
+                           "r"(z[10]), "r"(z[11]), "r"(z[12]), "r"(z[13]), "r"(z[14]), "r"(z[15]), "r"(tq + c) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    if (warp == 4 * TC_GROUPS + 1) {
+    if (warp == 4 * TC_GROUPS + TC_MMAW) {
         // ---- key stream
         if (lane == 0) {
             for (int st = 0; st < nsteps; st++) {
@@ -153,10 +181,10 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
                 tma_load_1d(ringB + (size_t)slot * TC_B_BYTES, kstream + (size_t)st * TC_B_BYTES, TC_B_BYTES, full + slot);
             }
         }
-    } else if (warp == 4 * TC_GROUPS) {
-        // ---- MMA issue
+    } else if (warp >= 4 * TC_GROUPS) {
+        // ---- MMA issue: issuer k takes the steps st = k (mod TC_MMAW)
         if (lane == 0) {
-            for (int st = 0; st < nsteps; st++) {
+            for (int st = warp - 4 * TC_GROUPS; st < nsteps; st += TC_MMAW) {
                 const int slot = st % TC_STAGES; const uint32_t ph = (uint32_t)(st / TC_STAGES) & 1u;
                 tc_wait(full + slot, ph);
                 tc_wait(ready + slot, ph);
@@ -164,7 +192,7 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
                 const uint64_t da = tc_desc(smem_u32(ringA + (size_t)slot * TC_A_BYTES), 2048);
                 const uint32_t sb = smem_u32(ringB + (size_t)slot * TC_B_BYTES);
 #pragma unroll
-                for (int h = 0; h < 2; h++) if (!(TC_DBG & 1)) tc_mma_i8(tmem + 256u * h, da, tc_desc(sb + 8192u * h, 4096), st > 0 ? 1u : 0u);
+                for (int h = 0; h < 2; h++) if (!(TC_DBG & 1)) tc_mma_i8(tmem + 256u * h, da, tc_desc(sb + 8192u * h, 4096), 1u);
                 if (TC_CLUSTER > 1) tc_commit_multicast(freeb + slot, (uint16_t)((1u << TC_CLUSTER) - 1u));
                 else tc_commit(freeb + slot);
             }
@@ -187,26 +215,22 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
         // refilled one coefficient at a time, so a step's digits come out by constant shifts -- no per-block counters and branches
         // (those, ~25 cycles of branch latency per block, were what bounded the base-4 instances: 8 blocks per step).
         // Input: a thread walking its own sample row touches one 32-byte sector per load and 32 different lines per warp instruction --
-        // with a new coefficient every step those loads alone cost a third of the gate key switch (ablation in profiles/r2_notes.md).
-        // There each warp reads its 32 samples in tiles of 32 coefficients with lane = coefficient (one coalesced row segment per
+        // those loads alone cost a third of the gate key switch and a quarter of the private one (ablations in profiles/r2_notes.md).
+        // Each warp reads its 32 samples in tiles of 32 coefficients with lane = coefficient (one coalesced row segment per
         // instruction), keeps the top 32 bits of a + prec_offset, and transposes the tile through shared memory; the next tile waits in
         // registers while the current one is used.
         const int cbits = BASEBIT * A.t;                              // bits per coefficient
         constexpr int SBITS = Q * BASEBIT;                            // bits per step
         int i_next = 0;                                               // next coefficient to enter the buffer
         uint64_t bitbuf = 0; int nbits = 0;
-        // TILED input (32-bit torus: one new coefficient per step at t = 8) or a per-thread register queue TC_PF coefficients deep
-        // (64-bit torus, a new coefficient every 2.5 steps: the strided loads are no burden there and the queue measured faster)
-        constexpr bool TILED = sizeof(TorusIn) == 4;
         uint32_t* tile = reinterpret_cast<uint32_t*>(tiles) + (size_t)warp * (32 * 33);
         const long s0w = (long)blockIdx.x * 128 + (m & ~31);         // first sample of this warp
         const TorusIn* inw = reinterpret_cast<const TorusIn*>(A.in);
-        uint32_t nxt[TILED ? 32 : 1];                                 // next tile: coefficient 32 c + lane of the warp's 32 samples
-        U raw_q[TILED ? 1 : TC_PF];
+        uint32_t nxt[32];                                             // next tile: coefficient 32 c + lane of the warp's 32 samples
         auto fetch_tile = [&](int c) {
             const int i = 32 * c + lane;
 #pragma unroll
-            for (int r = 0; r < (TILED ? 32 : 1); r++) {
+            for (int r = 0; r < 32; r++) {
                 U v = (U)0;
                 if (!(TC_DBG & 8) && s0w + r < A.count && i < A.rows_in) v = (U)inw[(size_t)(s0w + r) * A.in_stride + i];
                 nxt[r] = (uint32_t)((v + prec_offset) >> (W - 32));
@@ -215,25 +239,14 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
         auto store_tile = [&]() {
             __syncwarp();                                             // everybody has read the old tile
 #pragma unroll
-            for (int r = 0; r < (TILED ? 32 : 1); r++) tile[r * 33 + lane] = nxt[r];
+            for (int r = 0; r < 32; r++) tile[r * 33 + lane] = nxt[r];
             __syncwarp();
         };
-        if constexpr (TILED) { fetch_tile(0); store_tile(); fetch_tile(1); }
-        else {
-#pragma unroll
-            for (int x = 0; x < TC_PF; x++) raw_q[x] = (!(TC_DBG & 8) && live && x < A.rows_in) ? (U)in[x] : (U)0;
-        }
+        fetch_tile(0); store_tile(); fetch_tile(1);
         auto refill = [&]() {
+            if (i_next && (i_next & 31) == 0) { store_tile(); fetch_tile((i_next >> 5) + 1); }       // (warp-uniform: all lanes refill together)
             uint32_t a32 = 0u;                                        // past the last coefficient: zero digits (the tail of the last step)
-            if constexpr (TILED) {
-                if (i_next && (i_next & 31) == 0) { store_tile(); fetch_tile((i_next >> 5) + 1); }       // (warp-uniform: all lanes refill together)
-                if (live && i_next < A.rows_in) a32 = tile[(m & 31) * 33 + (i_next & 31)];
-            } else {
-                if (live && i_next < A.rows_in) a32 = (uint32_t)((raw_q[0] + prec_offset) >> (W - 32));
-#pragma unroll
-                for (int x = 0; x + 1 < TC_PF; x++) raw_q[x] = raw_q[x + 1];
-                raw_q[TC_PF - 1] = (!(TC_DBG & 8) && live && i_next + TC_PF < A.rows_in) ? (U)in[i_next + TC_PF] : (U)0;
-            }
+            if (live && i_next < A.rows_in) a32 = tile[(m & 31) * 33 + (i_next & 31)];
             i_next++;
             bitbuf |= (uint64_t)(a32 >> (32 - cbits)) << (64 - nbits - cbits);
             nbits += cbits;
@@ -245,35 +258,50 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
                 bitbuf <<= k; nbits -= k; n -= k;
             }
         };
-        drop(g * SBITS);                                              // group g starts at step g
-        for (int st = g; st < nsteps; st += TC_GROUPS) {
-            const int slot = st % TC_STAGES, use = st / TC_STAGES;
-            if (!(TC_DBG & 4)) { while (nbits < SBITS) refill(); }
-            uint32_t w[8];
+        // A group takes TC_SPT consecutive steps per turn: the slot wait, the stores, ONE proxy fence, one warp sync and the arrives are a
+        // chain of latencies (~500 cycles) that is paid per turn, not per step.
+        drop(g * TC_SPT * SBITS);                                     // group g starts at step g * TC_SPT
+        const uint32_t arow0 = smem_u32(ringA) + row_off;
+        for (int st0 = g * TC_SPT; st0 < nsteps; st0 += TC_GROUPS * TC_SPT) {
+            uint32_t w[TC_SPT][8];
 #pragma unroll
-            for (int x = 0; x < 8; x++) w[x] = 0u;
-            const uint32_t top = (uint32_t)(bitbuf >> 32);            // SBITS <= 16: the step's digits sit in the top word
+            for (int e = 0; e < TC_SPT; e++) {
+                if (!(TC_DBG & 4)) { while (nbits < SBITS) refill(); }
 #pragma unroll
-            for (int q = 0; q < Q; q++) {
-                const uint32_t d = (top >> (32 - (q + 1) * BASEBIT)) & (uint32_t)(BASE - 1);
-                // one-hot byte d-1 of this block's group of BASE bytes (nothing for d = 0)
-                if constexpr (BASE == 4) w[q] = (1u << (8 * d)) >> 8;
-                else if constexpr (BASE == 8) {
-                    const uint64_t v = d ? (uint64_t)1 << (8 * (d - 1)) : (uint64_t)0;
-                    w[2 * q] = (uint32_t)v; w[2 * q + 1] = (uint32_t)(v >> 32);
-                } else {                                            // BASE == 2: two bytes per block, candidate byte first
-                    w[q >> 1] |= d << (16 * (q & 1));
+                for (int x = 0; x < 8; x++) w[e][x] = 0u;
+                const uint32_t top = (uint32_t)(bitbuf >> 32);        // SBITS <= 16: the step's digits sit in the top word
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    const uint32_t d = (top >> (32 - (q + 1) * BASEBIT)) & (uint32_t)(BASE - 1);
+                    // one-hot byte d-1 of this block's group of BASE bytes (nothing for d = 0)
+                    if constexpr (BASE == 4) w[e][q] = (1u << (8 * d)) >> 8;
+                    else if constexpr (BASE == 8) {
+                        const uint64_t v = d ? (uint64_t)1 << (8 * (d - 1)) : (uint64_t)0;
+                        w[e][2 * q] = (uint32_t)v; w[e][2 * q + 1] = (uint32_t)(v >> 32);
+                    } else {                                        // BASE == 2: two bytes per block, candidate byte first
+                        w[e][q >> 1] |= d << (16 * (q & 1));
+                    }
+                }
+                bitbuf <<= SBITS; nbits -= SBITS;
+            }
+            if (!(TC_DBG & 4)) drop((TC_GROUPS - 1) * TC_SPT * SBITS);
+#pragma unroll
+            for (int e = 0; e < TC_SPT; e++) {
+                const int st = st0 + e;
+                if (st < nsteps) {
+                    const int slot = st % TC_STAGES, use = st / TC_STAGES;
+                    if (use > 0) tc_wait(freeb + slot, (uint32_t)(use - 1) & 1u);
+                    const uint32_t arow = arow0 + (uint32_t)slot * TC_A_BYTES;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(arow), "r"(w[e][0]), "r"(w[e][1]), "r"(w[e][2]), "r"(w[e][3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(arow + 2048u), "r"(w[e][4]), "r"(w[e][5]), "r"(w[e][6]), "r"(w[e][7]) : "memory");
                 }
             }
-            bitbuf <<= SBITS; nbits -= SBITS;
-            if (!(TC_DBG & 4)) drop((TC_GROUPS - 1) * SBITS);
-            if (use > 0) tc_wait(freeb + slot, (uint32_t)(use - 1) & 1u);
-            unsigned char* arow = ringA + (size_t)slot * TC_A_BYTES + row_off;
-            *reinterpret_cast<uint4*>(arow) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(arow + 2048) = make_uint4(w[4], w[5], w[6], w[7]);
             fence_proxy_async_smem();                               // generic-proxy stores -> visible to the tensor core's (async proxy) reads
             __syncwarp();
-            if (lane == 0) mbar_arrive(ready + slot);
+            if (lane == 0) {
+#pragma unroll
+                for (int e = 0; e < TC_SPT; e++) if (st0 + e < nsteps) mbar_arrive(ready + (st0 + e) % TC_STAGES);
+            }
         }
         // ---- epilogue: D[sample][column] of byte plane p sits in lane = sample, column 128 p + column
         tc_wait(done, 0);

@@ -18,7 +18,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:blin
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:keyswitch -c 1 -o $OUT/ks_${TAG} -f \
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline --gate-only > $OUT/ncu_ks_${TAG}.log 2>&1
 # circuit bootstrap at the BASELINE batch: the N=2048 blind rotation and the private key switch (second keyswitch launch of a step)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"blind_rotate_kernel|keyswitch_kernel" -c 3 -o $OUT/cb_${TAG} -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"blind_rotate_kernel|keyswitch" -c 3 -o $OUT/cb_${TAG} -f \
     python tests/dev/bench_cb.py 4096 nohp > $OUT/ncu_cb_${TAG}.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:hp_ -c 2 -o $OUT/hp_${TAG} -f \
     python tests/dev/bench_cb.py 0 hponly > $OUT/ncu_hp_${TAG}.log 2>&1

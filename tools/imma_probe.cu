@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(128) probe(int32_t* out, long long* cyc, int m
     __shared__ uint32_t tbase_s;
     __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(8) uint64_t ring[4];
+    __shared__ __align__(8) uint64_t ring2[16];
     extern __shared__ __align__(1024) unsigned char sm_raw[];
     unsigned char* sm = (unsigned char*)(((uintptr_t)sm_raw + 1023) & ~(uintptr_t)1023);
     const int NB = (mode & 1) ? 256 : 128, swz = (mode >> 1) & 1;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(128) probe(int32_t* out, long long* cyc, int m
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
         for (int i = 0; i < 4; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ring[i])) : "memory");
+        for (int i = 0; i < 16; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ring2[i])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes of A/B visible to the tensor core's reads
@@ -115,6 +117,57 @@ __global__ void __launch_bounds__(128) probe(int32_t* out, long long* cyc, int m
         }
         for (int s = nrep - 4 < 0 ? 0 : nrep - 4; s < nrep; s++) wait_bar(&ring[s & 3], (s >> 2) & 1);
         cyc[0] = clock64() - t0;
+        // the same MMAs, one commit per `cper` steps (mode bits 4-6), at most `nfl` commit groups in flight (mode bits 8-12):
+        // separates the cost of the commit itself from the depth of the queue the tensor pipe needs
+        const int cper = 1 << ((mode >> 4) & 7), nfl = (mode >> 8) & 31;
+        if (nfl > 0) {
+            const int ncommit = nrep / cper;
+            const long long t1 = clock64();
+            for (int c = 0; c < ncommit; c++) {
+                if (c >= nfl) wait_bar(&ring2[c % nfl], (uint32_t)((c / nfl) - 1) & 1u);
+                for (int q = 0; q < cper; q++)
+                    for (int p = 0; p < 512 / NB; p++) mma_i8(tbase + NB * p, da, db, idesc, 1);
+                commit(&ring2[c % nfl]);
+            }
+            for (int c = ncommit - nfl < 0 ? 0 : ncommit - nfl; c < ncommit; c++) wait_bar(&ring2[c % nfl], (uint32_t)(c / nfl) & 1u);
+            cyc[1] = clock64() - t1;
+        }
+    }
+    // several ISSUING threads (one per warp, mode bits 16-18 = how many), step s issued by warp s % nw, one commit per step on the
+    // issuer's own barriers: tcgen05.commit covers the committing thread's MMAs only, so every slot is still released by the thread that
+    // filled it; the integer accumulation does not care about the order in which the tensor core takes the two streams
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int nw = (mode >> 16) & 7;
+    if (nw > 0) {
+        const long long t2 = clock64();
+        if (w < nw && (threadIdx.x & 31) == 0) {
+            // zero the accumulators first (one MMA each, accumulate = 0, issued by warp 0 only) so the final sums are checkable
+            if (w == 0) { for (int p = 0; p < 512 / NB; p++) mma_i8(tbase + NB * p, da, db, idesc, 0); commit(&bar); }
+        }
+        if (w == 0 && (threadIdx.x & 31) == 0) { wait_bar(&bar, parity); parity ^= 1; }
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (w < nw && (threadIdx.x & 31) == 0) {
+            uint64_t* myring = ring2 + 4 * w;          // 4 barriers per issuer
+            int k = 0;
+            for (int s = w; s < nrep; s += nw, k++) {
+                if (k >= 4) wait_bar(&myring[k & 3], (uint32_t)((k >> 2) - 1) & 1u);
+                for (int p = 0; p < 512 / NB; p++) mma_i8(tbase + NB * p, da, db, idesc, 1);
+                commit(&myring[k & 3]);
+            }
+            for (int c = k - 4 < 0 ? 0 : k - 4; c < k; c++) wait_bar(&myring[c & 3], (uint32_t)(c >> 2) & 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) cyc[1] = clock64() - t2;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c = 0; c < 256; c += 16) {
+            uint32_t r[16];
+            TLD16(r, tbase + (((uint32_t)w * 32u) << 16) + c);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int i = 0; i < 16; i++) out[threadIdx.x * 256 + c + i] = (int32_t)r[i];
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -123,11 +176,16 @@ __global__ void __launch_bounds__(128) probe(int32_t* out, long long* cyc, int m
 
 int main() {
     int32_t* out; long long* cyc;
-    cudaMalloc(&out, 128 * 256 * 4); cudaMalloc(&cyc, 8);
+    cudaMalloc(&out, 128 * 256 * 4); cudaMalloc(&cyc, 16);
     int32_t* h = (int32_t*)malloc(128 * 256 * 4);
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
     const char* names[4] = {"N=128 x4, no swizzle", "N=256 x2, no swizzle", "N=128 x4, SWIZZLE_32B", "N=256 x2, SWIZZLE_32B"};
-    for (int mode = 0; mode < 4; mode++) {
+    const int cfgs[][2] = {{1, 4}, {1, 8}, {2, 4}, {4, 2}, {8, 2}, {16, 4}, {-1, 1}, {-1, 2}, {-1, 3}, {-1, 4}};      // (steps per commit, commit groups in flight) or (-1, issuing warps)
+    const int ncfg = sizeof(cfgs) / sizeof(cfgs[0]);
+    for (int mi = 0; mi < 4 + ncfg; mi++) {
+        int mode = mi;
+        if (mi >= 4 && cfgs[mi - 4][0] > 0) { int lg = 0; while ((1 << lg) < cfgs[mi - 4][0]) lg++; mode = 1 | (lg << 4) | (cfgs[mi - 4][1] << 8); }
+        if (mi >= 4 && cfgs[mi - 4][0] < 0) mode = 1 | (cfgs[mi - 4][1] << 16);
         cudaMemset(out, 0xff, 128 * 256 * 4);
         probe<<<1, 128, 32768>>>(out, cyc, mode, 4096);
         cudaError_t e = cudaDeviceSynchronize();
@@ -143,7 +201,21 @@ int main() {
                 for (int k = 0; k < 32; k++) ref += a_val(m, k) * b_val(n, k);
                 if (h[m * 256 + n] != 2 * ref) bad++;
             }
-        printf("%-24s mismatches %d of %d;  %.1f cycles per 512-column step\n", names[mode], bad, 128 * NB, (double)hc / 4096);
+        long long hc2 = 0; cudaMemcpy(&hc2, cyc + 1, 8, cudaMemcpyDeviceToHost);
+        if (mi < 4) printf("%-24s mismatches %d of %d;  %.1f cycles per 512-column step\n", names[mode & 3], bad, 128 * NB, (double)hc / 4096);
+        else if ((mode >> 16) & 7) {
+            int bad2 = 0;
+            for (int m = 0; m < 128; m++)
+                for (int n = 0; n < 256; n++) {
+                    int ref = 0;
+                    for (int k = 0; k < 32; k++) ref += a_val(m, k) * b_val(n, k);
+                    if (h[m * 256 + n] != 4097 * ref) bad2++;
+                }
+            printf("N=256 x2, %d issuing warps, one commit per step: %.1f cycles per 512-column step, %d mismatches of 32768 in the final sums\n",
+                   (mode >> 16) & 7, (double)hc2 / 4096, bad2);
+        }
+        else printf("N=256 x2, one commit per %2d steps, %2d commits (%3d steps) in flight: %.1f cycles per 512-column step\n", 1 << ((mode >> 4) & 7),
+                    (mode >> 8) & 31, ((mode >> 8) & 31) << ((mode >> 4) & 7), (double)hc2 / 4096);
     }
     return 0;
 }
