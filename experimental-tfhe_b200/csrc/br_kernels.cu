@@ -27,6 +27,9 @@
 #ifndef BR_SHARE_TW64
 #define BR_SHARE_TW64 0       // 1: Torus64 with stash keeps the per-lane twiddles ONCE per lane quarter, depth 9 included (measured slower: 196 vs 187 ms)
 #endif
+#ifndef BR_PRE0
+#define BR_PRE0 1
+#endif
 #ifndef BR_FASTDIGIT
 #define BR_FASTDIGIT 1
 #endif
@@ -172,14 +175,14 @@ __device__ __forceinline__ void load_tmem(cplx (&R)[16], const uint32_t taddr) {
 //             consumes it, chunk by chunk, the freed registers take BK[p][1] (12 warps per SM at 168 registers)
 //   KM_TMEM : they wait in tensor memory (KeyPipe, bk_pipe.cuh), no key registers at all (12 warps per SM)
 enum { KM_REGS2 = 0, KM_TMEM = 1, KM_REGS1 = 2 };
-template <int LOGM, bool FIRST, int KM, bool NOTT9 = false>
+template <int LOGM, bool FIRST, int KM, bool NOTT9 = false, bool PRE0 = false>
 __device__ __forceinline__ void forward_and_mac(cplx (&v)[16], const uint32_t tacc, const cplx* __restrict__ bkp,
                                                 cplx* __restrict__ buf, KeyPipe& kp,
                                                 const cplx* __restrict__ tw, const int t, const int bar_id, const uint32_t ttw) {
     typedef TreePlan<LOGM> P;
     if constexpr (KM == KM_REGS2) {
         Tw8Regs q;
-        tree_forward_a<LOGM>(v, buf, tw, t, bar_id, [&]() { tw8_issue(q, ttw); });      // depths 4-7 twiddles ride behind the transpose
+        tree_forward_a<LOGM, PRE0>(v, buf, tw, t, bar_id, [&]() { tw8_issue(q, ttw); });      // depths 4-7 twiddles ride behind the transpose
         tree_forward_b_tm(v, q);
     } else {
         tree_forward_a<LOGM>(v, buf, tw, t, bar_id);
@@ -514,6 +517,15 @@ __device__ __forceinline__ void cmux_step_mock(const int l, const int Bgbit, cpl
 // reload it and cut their digit.  Otherwise every level re-reads the accumulator.
 // PLAIN: the external product alone, ACC <- BK (x) ACC (tGswFFTExternMulToTLwe, cb/tgsw_functions.cpp:424-449): no rotation
 // on the way in, no accumulation on the way out.
+// The depth-0 butterfly of the forward transform multiplies its `hi` input by w(0,0) = (1 + i) / sqrt 2:
+//     w (x + i y) = ((x - y) + i (x + y)) / sqrt 2.
+// x and y are small integer digits here, so x - y and x + y are formed BEFORE the conversion to double, on the integer pipe, and the
+// butterfly shrinks from 6 to 4 FMAs (pass16's PRE0 form): -64 FP64 instructions per CMUX at l = 2.  Registers 8..15 of a lane (c >= 2)
+// are the `hi` inputs of depth 0.
+template <bool PRE0> __device__ __forceinline__ cplx digit_pair(const int c, const int dre, const int dim) {
+    if (PRE0 && c >= 2) return make_double2((double)(dre - dim), (double)(dre + dim));
+    return make_double2((double)dre, (double)dim);
+}
 template <int LOGM, typename Torus, bool STASH, int KM, bool PLAIN = false>
 __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, const cplx* __restrict__ bk,
                                           const int l, const int Bgbit, cplx* __restrict__ buf, const uint32_t tacc,
@@ -528,6 +540,9 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
     // (int32)(u * 2^(lev Bgbit) + 2^31) >> (32 - Bgbit): the multiply-add moves the field to the top (dropping the 2^31 folded in for level
     // 0) and flips its top bit.  Same values as ((u >> sh) & mask) - half, two integer instructions fewer per coefficient.
     constexpr bool FAST32 = sizeof(Torus) == 4 && BR_FASTDIGIT;
+    // digit pairs pre-combined for the depth-0 butterfly (digit_pair): N = 2048 only -- 188.8 -> 186.3 ms per 4,096 circuit bootstraps;
+    // the N = 1024 kernel got SLOWER with 64 FP64 instructions fewer per CMUX (356.1 vs 351.1 ms, profiles/r2_notes.md)
+    constexpr bool PRE0 = KM == KM_REGS2 && BR_PRE0 && sizeof(Torus) == 8;
     const U offset = (U)(decomp_offset((U)0, l, Bgbit) + (FAST32 ? (U)0x80000000u : (U)0));
     const uint32_t mask = (1u << Bgbit) - 1u;
     const int half = 1 << (Bgbit - 1);
@@ -560,11 +575,9 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
                            uim = (U)(((uint64_t)w[c][(4 * i + 3) % WPC] << 32) | w[c][(4 * i + 2) % WPC]); }
                     if constexpr (FAST32) {
                         const uint32_t mul = 1u << (lev * Bgbit);
-                        v[4 * c + i] = make_double2((double)((int32_t)((uint32_t)ure * mul + 0x80000000u) >> (32 - Bgbit)),
-                                                    (double)((int32_t)((uint32_t)uim * mul + 0x80000000u) >> (32 - Bgbit)));
+                        v[4 * c + i] = digit_pair<PRE0>(c, ((int32_t)((uint32_t)ure * mul + 0x80000000u) >> (32 - Bgbit)), ((int32_t)((uint32_t)uim * mul + 0x80000000u) >> (32 - Bgbit)));
                     } else
-                    v[4 * c + i] = make_double2((double)((int)((uint32_t)(ure >> sh) & mask) - half),
-                                                (double)((int)((uint32_t)(uim >> sh) & mask) - half));
+                    v[4 * c + i] = digit_pair<PRE0>(c, ((int)((uint32_t)(ure >> sh) & mask) - half), ((int)((uint32_t)(uim >> sh) & mask) - half));
                 }
         } else {
             int a2 = a;
@@ -578,14 +591,12 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
                     const U ure = (U)(PLAIN ? aq[j] : rot_minus_one<Torus, N>(aq, j, a2)) + offset;
                     const U uim = (U)(PLAIN ? aq[j + M] : rot_minus_one<Torus, N>(aq, j + M, a2)) + offset;
                     if constexpr (FAST32 && STASH) {          // with a stash this branch only ever sees level 0
-                        v[4 * c + i] = make_double2((double)((int32_t)(uint32_t)ure >> (32 - Bgbit)), (double)((int32_t)(uint32_t)uim >> (32 - Bgbit)));
+                        v[4 * c + i] = digit_pair<PRE0>(c, ((int32_t)(uint32_t)ure >> (32 - Bgbit)), ((int32_t)(uint32_t)uim >> (32 - Bgbit)));
                     } else if constexpr (FAST32) {
                         const uint32_t mul = 1u << (lev * Bgbit), add = lev ? 0x80000000u : 0u;
-                        v[4 * c + i] = make_double2((double)((int32_t)((uint32_t)ure * mul + add) >> (32 - Bgbit)),
-                                                    (double)((int32_t)((uint32_t)uim * mul + add) >> (32 - Bgbit)));
+                        v[4 * c + i] = digit_pair<PRE0>(c, ((int32_t)((uint32_t)ure * mul + add) >> (32 - Bgbit)), ((int32_t)((uint32_t)uim * mul + add) >> (32 - Bgbit)));
                     } else
-                    v[4 * c + i] = make_double2((double)((int)((uint32_t)(ure >> sh) & mask) - half),
-                                                (double)((int)((uint32_t)(uim >> sh) & mask) - half));
+                    v[4 * c + i] = digit_pair<PRE0>(c, ((int)((uint32_t)(ure >> sh) & mask) - half), ((int)((uint32_t)(uim >> sh) & mask) - half));
                     if (STASH) {
                         if (WPC == 8) { w[(2 * i) % WPC] = (uint32_t)ure; w[(2 * i + 1) % WPC] = (uint32_t)uim; }
                         else { w[(4 * i) % WPC] = (uint32_t)ure; w[(4 * i + 1) % WPC] = (uint32_t)((uint64_t)ure >> 32);
@@ -603,8 +614,8 @@ __device__ __forceinline__ void cmux_step(Torus* __restrict__ acc, const int a, 
         // depth-9 twiddles (N = 2048) come from shared memory only where the Torus64 stash has taken their tensor-memory columns and the
         // twiddles are not shared per lane quarter
         constexpr bool NOTT9 = STASH && sizeof(Torus) == 8 && !(BR_SHARE_TW64 && KM == KM_REGS2);
-        if (p == 0) forward_and_mac<LOGM, true, KM, NOTT9>(v, tacc, bk, buf, kp, tw, t, bar_id, ttw);
-        else        forward_and_mac<LOGM, false, KM, NOTT9>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp, tw, t, bar_id, ttw);
+        if (p == 0) forward_and_mac<LOGM, true, KM, NOTT9, PRE0>(v, tacc, bk, buf, kp, tw, t, bar_id, ttw);
+        else        forward_and_mac<LOGM, false, KM, NOTT9, PRE0>(v, tacc, bk + (size_t)(p * 2) * M, buf, kp, tw, t, bar_id, ttw);
     }
     // every lane has finished reading the accumulator once it passes the first sync inside the backward transform
     if constexpr (KM == KM_REGS2) {

@@ -186,9 +186,19 @@ __device__ __forceinline__ void tw8_to_tmem(const cplx (&E)[8], const uint32_t t
 }
 
 // four tree depths on the 16 registers of a lane; E = the 8 essential twiddles of these depths
-template <bool INV> __device__ __forceinline__ void pass16(cplx (&v)[16], const cplx* __restrict__ E, const int estride) {
+// PRE0 (forward, depth 0 only): the caller has already formed (x - y, x + y) of every `hi` input, w(0,0) = (1 + i) c with c = 1/sqrt 2
+template <bool INV, bool PRE0 = false> __device__ __forceinline__ void pass16(cplx (&v)[16], const cplx* __restrict__ E, const int estride) {
     if (!INV) {
-        {   const cplx w = E[0];
+        if constexpr (PRE0) {
+            const double c = E[0].x;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const double s = v[i + 8].x, t = v[i + 8].y;
+                v[i + 8].x = fma(-c, s, v[i].x); v[i + 8].y = fma(-c, t, v[i].y);
+                v[i].x = fma(c, s, v[i].x);      v[i].y = fma(c, t, v[i].y);
+            }
+        } else {
+            const cplx w = E[0];
 #pragma unroll
             for (int i = 0; i < 8; i++) bf_fwd(v[i], v[i + 8], w); }
         {   const cplx w = E[estride];
@@ -243,12 +253,12 @@ template <int LOGM> __device__ __forceinline__ int tree_side(const int t) {     
 //          out v[i] = spectrum slot i of this lane (leaf order, private)
 // Split in two so the caller can reuse the transpose buffer between the halves (after part A nobody reads buf any more).
 struct TreeNoHook { __device__ __forceinline__ void operator()() const {} };
-template <int LOGM, typename Hook = TreeNoHook>
+template <int LOGM, bool PRE0 = false, typename Hook = TreeNoHook>
 __device__ __forceinline__ void tree_forward_a(cplx (&v)[16], cplx* __restrict__ buf, const cplx* __restrict__ tw, const int t, const int bar_id,
                                                Hook mid = Hook()) {
     typedef TreePlan<LOGM> P;
     constexpr int T = P::T;
-    pass16<false>(v, reinterpret_cast<const cplx*>(c_tree_ta), 1);
+    pass16<false, PRE0>(v, reinterpret_cast<const cplx*>(c_tree_ta), 1);
     TL(2);
     lanes_sync<T>(bar_id);                                   // WAR: earlier reads of buf
 #pragma unroll
