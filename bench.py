@@ -113,13 +113,15 @@ CB_BATCH = 4096
 
 
 def _tensor_peak_tops():
-    """int8 dense peak = 2 x the bf16 dense peak (same tensor cores, half the operand width); the bf16 figure is the measured one
-    of MEASURED_PEAKS.json (sustained: the key switch runs inside a long step), else the profiling recipe's nominal 2250."""
+    """int8 peak of the tensor pipe as measured by tools/imma_probe.cu (profiles/r2_imma_probe3.txt): a 128 x 256 x 32 u8 MMA retires in
+    128 cycles when three warps keep the pipe fed = 8192 MAC per clock per SM; x 148 SMs x the SM clock of MEASURED_PEAKS.json (the key
+    switch does not pull the clock down the way a long bf16 GEMM does, so 2 x bf16_tflops would under-state it)."""
+    mhz = 1965.0
     try:
-        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        return 2.0 * float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"])), "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 = 2 x bf16 rate)"
+        mhz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("sm_max_mhz", mhz))
     except Exception:
-        return 4500.0, "fallback: nominal 4.5 POP/s int8 dense (B200_PROFILING.md)"
+        pass
+    return 2.0 * 8192 * 148 * mhz * 1e6 / 1e12, f"probe-measured 8192 u8 MAC/clk/SM (tools/imma_probe.cu) x 148 SMs x {mhz:.0f} MHz"
 
 
 def _ks_tensor_roofline(kernel, samples, rows, t, basebit, cols_pad, nz, ms):

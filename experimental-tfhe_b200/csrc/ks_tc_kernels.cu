@@ -131,8 +131,15 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = A.rows_in * A.t;
     const int nsteps = (nblk + Q - 1) / Q;
+    // CTA order.  gridDim.y > 1: sample tiles vary fastest -- the CTAs of a wave walk the same key stream together (a key image that does
+    // not fit the L2 is then read from HBM once).  gridDim.y == 1: column groups vary fastest -- the CTAs that share a sample tile run
+    // together and its input rows come from HBM once (key image L2-resident: the gate key switch read its 268 MB of input four times
+    // before, 1.5 GB of DRAM traffic per launch against 0.46 GB algorithmic).
+    const int ncg = A.cols_pad / 128;
+    const int cgrp = gridDim.y > 1 ? (int)blockIdx.y : (int)(blockIdx.x % ncg);
+    const long tile_idx = gridDim.y > 1 ? (long)blockIdx.x : (long)(blockIdx.x / ncg);
     const unsigned char* kstream = reinterpret_cast<const unsigned char*>(A.key) + (size_t)blockIdx.z * A.key_z_stride * sizeof(int32_t) +
-                                   (size_t)blockIdx.y * nsteps * TC_B_BYTES;
+                                   (size_t)cgrp * nsteps * TC_B_BYTES;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(full + s, 1); mbar_init(ready + s, 4); mbar_init(freeb + s, TC_CLUSTER); }
@@ -205,7 +212,7 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
         //      chain, not the tensor core (492 cycles per step), set the pace, and splitting each ROW between two threads changed nothing
         //      (profiles/r2_notes.md).  Taking turns step by step gives every warp TC_GROUPS step times per row.
         const int m = threadIdx.x & 127, g = threadIdx.x >> 7;
-        const long smp = (long)blockIdx.x * 128 + m;
+        const long smp = tile_idx * 128 + m;
         const bool live = smp < A.count;
         const TorusIn* in = reinterpret_cast<const TorusIn*>(A.in) + (size_t)(live ? smp : 0) * A.in_stride;
         const U prec_offset = (U)1 << (W - (1 + BASEBIT * A.t));      // cb/lwe_functions.cpp:141 ; poc:444,674
@@ -224,7 +231,7 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
         int i_next = 0;                                               // next coefficient to enter the buffer
         uint64_t bitbuf = 0; int nbits = 0;
         uint32_t* tile = reinterpret_cast<uint32_t*>(tiles) + (size_t)warp * (32 * 33);
-        const long s0w = (long)blockIdx.x * 128 + (m & ~31);         // first sample of this warp
+        const long s0w = tile_idx * 128 + (m & ~31);                  // first sample of this warp
         const TorusIn* inw = reinterpret_cast<const TorusIn*>(A.in);
         uint32_t nxt[32];                                             // next tile: coefficient 32 c + lane of the warp's 32 samples
         auto fetch_tile = [&](int c) {
@@ -309,7 +316,7 @@ __global__ void __cluster_dims__(TC_CLUSTER, 1, 1) __launch_bounds__(TC_THREADS,
         const uint32_t tl = tmem + (((uint32_t)(warp & 3) * 32u) << 16);        // warps w and w + 4 reach the same lane quarter
         int32_t* orow = nullptr;
         if (live) orow = A.out + (size_t)blockIdx.z * A.out_z_stride + (size_t)(smp / A.group) * A.out_stride + (size_t)(smp % A.group) * A.out_inner;
-        const int colbase = blockIdx.y * 128;
+        const int colbase = cgrp * 128;
 #pragma unroll 1
         for (int c = (128 / TC_GROUPS) * g; c < (128 / TC_GROUPS) * (g + 1); c += 16) {       // each of the sample's threads stores its share of the columns
             uint32_t p0[16], p1[16], p2[16], p3[16];
@@ -342,7 +349,11 @@ static cudaError_t launch_ks_tc_b(const KSArgs& a, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         attr_done.done();
     }
-    dim3 grid(((a.count + 127) / 128 + TC_CLUSTER - 1) / TC_CLUSTER * TC_CLUSTER, a.cols_pad / 128, a.nz > 0 ? a.nz : 1);
+    const int tiles = ((a.count + 127) / 128 + TC_CLUSTER - 1) / TC_CLUSTER * TC_CLUSTER, ncg = a.cols_pad / 128;
+    // key image per launch small enough to stay in the L2 (and more than one column group, no clusters): column groups fastest
+    const bool cg_fast = TC_CLUSTER == 1 && ncg > 1 && ks_key_bytes(a.rows_in, a.t, a.basebit, a.cols_pad) * (size_t)(a.nz > 0 ? a.nz : 1) <= ((size_t)96 << 20) &&
+                         (long)tiles * ncg <= 0x7fffffffL;
+    dim3 grid(cg_fast ? tiles * ncg : tiles, cg_fast ? 1 : ncg, a.nz > 0 ? a.nz : 1);
     keyswitch_tc_kernel<TorusIn, BASEBIT><<<grid, TC_THREADS, TC_SMEM, s>>>(a);
     return cudaGetLastError();
 }
