@@ -914,19 +914,27 @@ template <int LOGM, typename Torus, int GROUPS, bool STASH, int KM, int F2 = 0> 
     blind_rotate_kernel<LOGM, Torus, GROUPS, STASH, KM, F2><<<grid, GROUPS * TreePlan<LOGM>::T, BRSmem<LOGM, Torus, GROUPS, STASH, KM>::TOTAL, s>>>(a);
     return cudaGetLastError();
 }
+// The measured alternatives (keytm, half, nostash, pairs, the ceiling probe) are instantiated only in development builds
+// (-DBR_EXPERIMENTS=1, tools/build_alt.sh): the product library carries the two kernels it runs.  Asking for a variant the library
+// was built without is an error, not a silent fallback.
+#ifndef BR_EXPERIMENTS
+#define BR_EXPERIMENTS 0
+#endif
 cudaError_t blind_rotate_init() {
     cudaError_t e;
+    if ((e = br_attr<9, int32_t, G32, true, KM_REGS2>()) != cudaSuccess) return e;
+    if ((e = br_attr<10, int64_t, G64, true, KM_REGS2>()) != cudaSuccess) return e;
+#if BR_EXPERIMENTS
     if ((e = br_attr<9, int32_t, G32_KP, false, KM_TMEM>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32_KP, true, KM_REGS1>()) != cudaSuccess) return e;
-    if ((e = br_attr<9, int32_t, G32, true, KM_REGS2>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32, false, KM_REGS2>()) != cudaSuccess) return e;
     if ((e = br_attr<10, int64_t, G64, false, KM_REGS2>()) != cudaSuccess) return e;
-    if ((e = br_attr<10, int64_t, G64, true, KM_REGS2>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, 4, true, KM_REGS2, 9>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32, true, KM_REGS2, 9>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32, true, KM_REGS2, 2>()) != cudaSuccess) return e;
     if ((e = br_attr<9, int32_t, G32, true, KM_REGS2, 3>()) != cudaSuccess) return e;
     if ((e = br_attr<10, int64_t, G64, true, KM_REGS2, 3>()) != cudaSuccess) return e;
+#endif
     g_inited.done();
     return cudaSuccess;
 }
@@ -934,20 +942,25 @@ cudaError_t blind_rotate_init() {
 cudaError_t launch_blind_rotate32(const BRArgs& a, cudaStream_t s) {
     if (g_inited.need()) { cudaError_t e = blind_rotate_init(); if (e != cudaSuccess) return e; }
     if (a.count <= 0) return cudaSuccess;
-    // development knob: TFHE_B200_BR_VARIANT = keytm | half | nostash selects the measured alternatives
+    // development knob: TFHE_B200_BR_VARIANT = keytm | half | nostash | 2 | 3 | m | M selects the measured alternatives
     static const char* variant = getenv("TFHE_B200_BR_VARIANT");
-    if (variant && variant[0] == 'k') return br_launch<9, int32_t, G32_KP, false, KM_TMEM>(a, a.count, s);
-    if (variant && variant[0] == 'h') return br_launch<9, int32_t, G32_KP, true, KM_REGS1>(a, a.count, s);
-    if (variant && variant[0] == 'n') return br_launch<9, int32_t, G32, false, KM_REGS2>(a, a.count, s);
-    // "pairs": two digit polynomials per pass (cmux_step2), rolling key window of 2 / 3 slots.  Measured 380 / 382 ms against 354 ms
-    // for the default (profiles/r2_notes.md): what the side-by-side transforms gain (short_scoreboard 10.3 -> 5.9 %) the exposed
-    // key latency in the multiply-accumulate gives back (long_scoreboard 1.4 -> 7.6 %), and 255 registers leave a few spills.
-    if (variant && variant[0] == 'm') return br_launch<9, int32_t, 4, true, KM_REGS2, 9>(a, a.count, s);           // ceiling probe, 4 warps per SM
-    if (variant && variant[0] == 'M') return br_launch<9, int32_t, G32, true, KM_REGS2, 9>(a, a.count, s);         // ceiling probe, 8 warps per SM
-    // (a variant that deferred the multiply-accumulates of polynomial p into the transpose of p+1 -- spectrum parked in tensor memory --
-    //  was correct and 22 % slower: profiles/r2_notes.md, commit "Experiment (negative): multiply-accumulates ... deferred")
-    if (variant && variant[0] == '2') return br_launch<9, int32_t, G32, true, KM_REGS2, 2>(a, a.count, s);
-    if (variant && variant[0] == '3') return br_launch<9, int32_t, G32, true, KM_REGS2, 3>(a, a.count, s);
+    if (variant && variant[0] && variant[0] != 's' && variant[0] != 'd') {
+#if BR_EXPERIMENTS
+        if (variant[0] == 'k') return br_launch<9, int32_t, G32_KP, false, KM_TMEM>(a, a.count, s);
+        if (variant[0] == 'h') return br_launch<9, int32_t, G32_KP, true, KM_REGS1>(a, a.count, s);
+        if (variant[0] == 'n') return br_launch<9, int32_t, G32, false, KM_REGS2>(a, a.count, s);
+        // "pairs": two digit polynomials per pass (cmux_step2), rolling key window of 2 / 3 slots.  Measured 380 / 382 ms against 354 ms
+        // for the default (profiles/r2_notes.md): what the side-by-side transforms gain (short_scoreboard 10.3 -> 5.9 %) the exposed
+        // key latency in the multiply-accumulate gives back (long_scoreboard 1.4 -> 7.6 %), and 255 registers leave a few spills.
+        if (variant[0] == '2') return br_launch<9, int32_t, G32, true, KM_REGS2, 2>(a, a.count, s);
+        if (variant[0] == '3') return br_launch<9, int32_t, G32, true, KM_REGS2, 3>(a, a.count, s);
+        if (variant[0] == 'm') return br_launch<9, int32_t, 4, true, KM_REGS2, 9>(a, a.count, s);           // ceiling probe, 4 warps per SM
+        if (variant[0] == 'M') return br_launch<9, int32_t, G32, true, KM_REGS2, 9>(a, a.count, s);         // ceiling probe, 8 warps per SM
+        // (a variant that deferred the multiply-accumulates of polynomial p into the transpose of p+1 -- spectrum parked in tensor memory --
+        //  was correct and 22 % slower: profiles/r2_notes.md, commit "Experiment (negative): multiply-accumulates ... deferred")
+#endif
+        return cudaErrorNotSupported;        // unknown variant, or a library built without -DBR_EXPERIMENTS=1
+    }
     return br_launch<9, int32_t, G32, true, KM_REGS2>(a, a.count, s);
 }
 cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
@@ -956,9 +969,11 @@ cudaError_t launch_blind_rotate64(const BRArgs& a, cudaStream_t s) {
     const long units = (long)a.count * (a.n_mu > 0 ? a.n_mu : 1);
     // Torus64: the stash takes 64 columns, so the depth-9 twiddles stay in shared memory (R 128 | stash 64 | twiddles 64 = 256 columns).
     // With the waits deferred the stash pays here too (189 vs 201 ms per 4096 circuit bootstraps; before that it cost 3 %).
+#if BR_EXPERIMENTS
     static const char* variant = getenv("TFHE_B200_BR_VARIANT");
     if (variant && variant[0] == 'n') return br_launch<10, int64_t, G64, false, KM_REGS2>(a, units, s);      // "nostash"
     if (variant && variant[0] == '3') return br_launch<10, int64_t, G64, true, KM_REGS2, 3>(a, units, s);    // "pairs": 196 vs 188 ms
+#endif
     return br_launch<10, int64_t, G64, true, KM_REGS2>(a, units, s);
 }
 

@@ -253,6 +253,11 @@ print("OK")
 '''
     env = dict(os.environ, TFHE_B200_BR_VARIANT="keytm")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # the measured alternatives are compiled only into development builds (-DBR_EXPERIMENTS=1, tools/build_alt.sh experiments br_kernels)
+    alt = os.path.join(root, "tools", "alt", "libtfhe_b200_experiments.so")
+    if not os.path.exists(alt):
+        pytest.skip("no development build with the experimental blind-rotation variants (tools/alt/libtfhe_b200_experiments.so)")
+    env["TFHE_B200_LIB"] = alt
     r = subprocess.run([sys.executable, "-c", code, root], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
 
