@@ -1,4 +1,6 @@
-// ks_kernels.cu -- batched key switching as a tiled gather-accumulate.
+// ks_kernels.cu -- batched key switching as a tiled gather-accumulate on the CUDA cores.
+// (Selected with TFHE_B200_KS=cuda.  The default path is the tensor-core kernel of ks_tc_kernels.cu, 5x faster and bit-identical;
+//  this is the form the design started from and the yardstick the tensor-core kernel was measured against.)
 //
 // Replaces lweKeySwitch / lweKeySwitchTranslate_fromArray (cb/lwe_functions.cpp:136-171), preKeySwitch
 // (cb/poc_CircuitBootstrapping.cpp:437-465) and circuitPrivKS (:667-698):

@@ -10,14 +10,16 @@
 // and the recombination mod 2^32 is the same wrap-around arithmetic the reference's additions perform, so results are bit-identical.
 // The one-hot form wastes base-1 of every base multiplies, and still wins by a wide margin: the CUDA-core kernel is bound by the
 // shared-memory bandwidth that feeds the selected rows to the integer adders (one 128-byte wavefront per 32 additions), the tensor core
-// takes 128 samples x 128 columns x 32 key rows per instruction (tools/imma_probe.cu: 120 cycles per 128x128x32 MMA, profiles/r2_notes.md).
+// takes 128 samples x 256 columns (two byte planes) x 32 key rows per instruction, 128 cycles each when the pipe is kept fed
+// (tools/imma_probe.cu, profiles/r2_imma_probe3.txt, profiles/r2_notes.md).
 //
 // One CTA = 128 samples (the M dimension = the 128 lanes of tensor memory) x 128 output columns, four s32 accumulator tiles of
 // 128 columns (one per key byte) = all 512 columns of tensor memory.  A STEP covers 32 rows of the one-hot matrix = 32 / base
 // consecutive (i, j) blocks (a group of `base` rows per block: base-1 candidates and one padding row that no digit selects).
-//   producer warps (4 per group, TC_GROUPS groups taking turns step by step): thread = sample: read a_i, cut the digits, write the step's
-//                32-byte one-hot row into the A ring (K-major, no swizzle); at the end read the four tiles back, recombine, negate, add b,
-//                store (each group its share of the columns)
+//   producer warps (4 per group, TC_GROUPS groups taking turns, TC_SPT steps per turn): thread = sample: input coefficients arrive in
+//                coalesced 32 x 32 tiles transposed through shared memory, a step's digits are cut from a bit stream, its 32-byte one-hot
+//                row goes into the A ring (K-major, no swizzle); at the end read the four tiles back, recombine, negate, add b, store
+//                (each group its share of the columns)
 //   MMA warps  : TC_MMAW issuing threads taking turns step by step: the two MMAs of a step (same A, the two plane pairs of the key as B),
 //                committed to the slot's `free` barrier
 //   TMA warp   : one thread streams the key: one 16 KB bulk copy per step into the B ring
