@@ -1,0 +1,5 @@
+set -u
+mkdir -p gpurun_out
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 5 --warmup 3 > gpurun_out/bench_r2h_n4.json 2> gpurun_out/bench_r2h_n4.err
+tail -c 300 gpurun_out/bench_r2h_n4.err
+cut -c1-300 gpurun_out/bench_r2h_n4.json
